@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py — shared_tree build throughput (Gbp/s) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--bases 3100000000] [--repeat-permille 500] [--seed 42]
+
+A "step" is one full shared_tree build (pack + canonicalise + hash-cons every level, ids
+final) of the synthetic genome-shaped sequence of BASELINE.json config 3 (`--bases`
+random ACGT + planted repeats).  `value` = bases / device time with the
+ASCII body already resident in HBM; `e2e` = the same build through the public C-ABI call
+with the text in pinned HOST memory (H2D inside the timed region, result counters read
+back).  One JSON line on stdout.
+
+--impl reference times the reference's own CPU build (oracle/_ref when it was compiled,
+else the oracle port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DNA = 12
+METRIC = "shared_tree_build_gbp_per_s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bases", type=int, default=3_100_000_000)
+    ap.add_argument("--repeat-permille", type=int, default=500)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-sample-bases", type=int, default=0, help="0 = auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {
+        "workload": "config 3: synthetic human-genome-shaped sequence, random ACGT + planted repeats, one shared_tree build",
+        "bases": args.bases, "dna_size": DNA, "repeat_permille": args.repeat_permille, "seed": args.seed,
+        "repeat_lengths": "300*2^k+r, k in 0..9, capped at 200000",
+        "repeat_alignment": "4/8 forward at a multiple of 12*1024 bases, 1/8 reverse-complement aligned, 3/8 arbitrary",
+        "l2_policy": "inputs (>= 1 B/base of text + multi-GB tables) are far larger than the 126 MB L2",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_build_once(text: bytes):
+    """Times one CPU build of `text` with the unmodified reference when it is available
+    (oracle/_ref/libref.so: shared_tree{path}, i.e. loader thread + build thread exactly as
+    ./compress runs it), else with the oracle port.  Returns (seconds, kind, cores)."""
+    from oracle import pyoracle
+    if pyoracle.have_ref():
+        ref = pyoracle.Ref()
+        with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
+            f.write(text)
+            path = f.name
+        try:
+            t0 = time.perf_counter()
+            tree = ref.build_file(path, DNA)
+            dt = time.perf_counter() - t0
+            assert tree.width() == len(text) // DNA
+        finally:
+            os.unlink(path)
+        return dt, "reference", 2  # one build thread + one loader thread (NullMutex hash maps)
+    orc = pyoracle.Oracle()
+    t0 = time.perf_counter()
+    leaves = orc.fasta_to_leaves(text, DNA)
+    orc.build(leaves, DNA)
+    return time.perf_counter() - t0, "port", 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    orc = pyoracle.Oracle()
+    sample = args.cpu_sample_bases or 24_000_000
+    sample = min(sample, args.bases)
+    text = orc.synth(args.bases, args.seed, args.repeat_permille, first=0, count=sample).tobytes()
+    for _ in range(args.warmup):
+        cpu_build_once(text[: max(DNA * 1024, sample // 16)])
+    times = []
+    kind, cores = "port", 1
+    for _ in range(args.steps):
+        dt, kind, cores = cpu_build_once(text)
+        times.append(dt)
+    total = sum(times)
+    value = sample * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, {"sample": f"first {sample} bases of the {args.bases}-base sequence per step"}),
+        "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": cores, "kind": kind,
+                         "sample": f"first {sample} bases, {len(times)} timed builds", "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(n0: int, leaf_unique: int, layer_unique: list[int]):
+    """Compulsory HBM bytes per kernel class for one build: streams only;
+    hash-table probes are reported separately as non-compulsory traffic."""
+    levels = [n0]
+    while levels[-1] > 1 or len(levels) == 1:
+        levels.append((levels[-1] + 1) // 2)
+    node_pos = levels[1:]
+    uniq = [leaf_unique] + list(layer_unique)
+    pos = [n0] + node_pos
+    out = {
+        "leaf_insert": n0 * DNA + 4 * n0,
+        "node_insert": sum(4 * a + 4 * b for a, b in zip(levels[:-1], levels[1:])),
+        "count_first": sum(4 * p + p // 8 for p in pos),
+        "assign_ids": sum(p // 8 + 16 * u for p, u in zip(pos, uniq)),
+        "resolve_ids": sum(p // 8 + 8 * (p - u) for p, u in zip(pos, uniq)),
+    }
+    out["build_total"] = sum(out.values())
+    return out
+
+
+# ---------------------------------------------------------------------------- own arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("multi-GPU sharded build: see bench_multi (not wired in this revision)")
+    torch.cuda.set_device(local_rank)
+    pkg = load_package()
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peak_gbs, peak_src = 6650.0, "fallback"
+    if peaks_path.exists():
+        peak_gbs, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
+
+    n_bases = args.bases
+    stream = torch.cuda.current_stream()
+    text = torch.empty(n_bases, dtype=torch.uint8, device="cuda")
+    pkg.synth_genome(text, n_bases, seed=args.seed, repeat_permille=args.repeat_permille, device=local_rank,
+                     stream=stream.cuda_stream)
+    tree = pkg.SharedTree(DNA, device=local_rank, stream=stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        tree.build_from_body(text)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = pkg.kernel_launches()
+    tree.profile(True)
+    tree.profile_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        tree.build_from_body(text)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = ev0.elapsed_time(ev1)
+    prof = tree.profile_read()
+    tree.profile(False)
+    launches = pkg.kernel_launches() - launches0
+    ms_per_step = total_ms / args.steps
+    bases_used = tree.width() * DNA
+    value = bases_used / (ms_per_step * 1e-3) / 1e9
+
+    n0 = tree.width()
+    counts = tree.layer_counts()
+    alg = algorithmic_bytes(n0, tree.leaf_count(), counts)
+    kernels = {}
+    for name, rec in prof.items():
+        per_step_ms = rec["ms"] / args.steps
+        k = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": rec["launches"] // args.steps}
+        if name in alg and per_step_ms > 0:
+            k["algorithmic_bytes"] = alg[name]
+            k["achieved_gbs"] = round(alg[name] / (per_step_ms * 1e-3) / 1e9, 1)
+            k["frac_of_peak"] = round(k["achieved_gbs"] / peak_gbs, 4)
+        kernels[name] = k
+    timed = {n: k for n, k in kernels.items() if "algorithmic_bytes" in k}
+    dom = max(timed, key=lambda n: timed[n]["ms_per_step"])
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        traffic = json.loads(tpath.read_text()).get(dom)
+    roofline = {
+        "bound": "hbm", "kernel": dom,
+        "achieved": timed[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
+        "frac": round(timed[dom]["achieved_gbs"] / peak_gbs, 4), "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_step": timed[dom]["algorithmic_bytes"],
+        "launches_per_step": timed[dom]["launches_per_step"],
+        "avg_launch_ms": round(timed[dom]["ms_per_step"] / max(1, timed[dom]["launches_per_step"]), 4),
+        "whole_build": {"algorithmic_bytes": alg["build_total"],
+                        "achieved": round(alg["build_total"] / (ms_per_step * 1e-3) / 1e9, 1),
+                        "frac": round(alg["build_total"] / (ms_per_step * 1e-3) / 1e9 / peak_gbs, 4)},
+    }
+
+    # ---- end to end: pinned host text -> C-ABI build -> counters back on the host ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
+        host.copy_(text)
+        torch.cuda.synchronize()
+        tree.build_from_body(host)  # warm the staging allocation
+        t0 = time.perf_counter()
+        reps = max(1, min(args.steps, 3))
+        for _ in range(reps):
+            tree.build_from_body(host)
+            _ = (tree.width(), tree.leaf_count(), tree.node_count(), tree.root())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        e2e = {"value": bases_used / dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": n_bases,
+               "d2h_bytes_per_step": 4 * (len(counts) + 1) + 4 + 16, "ms_per_step": dt * 1e3, "steps": reps}
+        del host
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sample = args.cpu_sample_bases or 120_000_000
+        sample = min(sample, n_bases)
+        chunk = text[:sample].cpu().numpy().tobytes()
+        dt, kind, cores = cpu_build_once(chunk)
+        cpu = {"value": sample / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": kind,
+               "sample": f"first {sample} bases of the same sequence, one build, {dt:.1f} s", "host_cpus": os.cpu_count()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+        "tree": {"width": n0, "leaves": tree.leaf_count(), "nodes": tree.node_count(), "depth": tree.depth()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,478 @@
+// build.cu — level-by-level bottom-up construction of the shared tree (hash-consing).
+//
+// Replaces tree_constructor (reference include/shared_tree.h:245-316,
+// src/shared_tree.cpp:621-763) and the phmap dedup behind it.  The reference
+// streams 2^22-leaf segments through per-layer hash maps, one element at a time;
+// because its segments are powers of two that is equivalent to ONE global pass per
+// level, which is what runs here:
+//
+//   per level (leaves, then node layers bottom-up):
+//     insert   every position canonicalises its item and lowers the item's
+//              min-position in an open-addressing table (or a direct-addressed
+//              table for ACGT-only leaves)                     [random HBM/L2]
+//     count    position p is a first occurrence iff minpos == p -> bitmask +
+//              per-CTA counts                                  [random read]
+//     scan     exclusive scan of the per-CTA counts           [tiny]
+//     assign   first occurrences get id = rank, publish it in the table, append
+//              the item to the layer in id order, emit their pointer
+//     resolve  the other positions fetch the id                [random read]
+//
+// IDs are first-occurrence ranks in position order, independent of which thread won
+// which atomic, so the result equals the reference's sequential emplace order.
+#include <algorithm>
+
+#include "pack.cuh"
+#include "tree.h"
+
+namespace stb {
+
+constexpr int LVL_THREADS = 256;
+constexpr int LVL_ITERS = 4;
+constexpr int LVL_TILE = LVL_THREADS * LVL_ITERS;  // positions per CTA in count/assign/resolve
+
+struct LevelTable {
+  Slot* slots;        // hash mode: cap + 1 slots
+  uint32_t* dminpos;  // direct mode: 4^S entries each
+  uint32_t* dids;
+  uint32_t cap;
+};
+
+struct BuildFlags {
+  unsigned long long bad_symbol;  // (byte offset << 8) | upper-cased byte; ~0 = none
+  uint32_t non_acgt;              // direct leaf mode met a non-ACGT leaf
+  uint32_t bad_leaf;              // packed input leaf with bits >= 4S
+};
+
+template <bool DIRECT>
+__device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_t pos, const LevelTable& tab,
+                                            uint32_t* __restrict__ tmp, BuildFlags* flags) {
+  uint32_t f;
+  const unsigned long long canon = canonical_leaf(v, S, f);
+  uint32_t s;
+  if (DIRECT) {
+    if (!leaf_is_acgt(v, S)) {
+      flags->non_acgt = 1u;
+      tmp[pos] = 0u;
+      return;
+    }
+    s = leaf_to_2bit(canon);
+    if (__ldcg(tab.dminpos + s) > pos) atomicMin(tab.dminpos + s, pos);
+  } else {
+    s = table_insert(tab.slots, tab.cap, canon, pos);
+  }
+  tmp[pos] = s | f;
+}
+
+// Leaves straight from the ASCII body: pack (dna.cpp:79-84) + canonical (dna.cpp:135)
+// + emplace_leaf (shared_tree.cpp:630) fused; the packed leaves never touch HBM.
+template <int S_T, bool DIRECT>
+__global__ void __launch_bounds__(PACK_THREADS)
+leaf_insert_text_kernel(const char* __restrict__ body, uint64_t n_leaves, int S_rt, LevelTable tab,
+                        uint32_t* __restrict__ tmp, BuildFlags* flags) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* lut = smem;
+  uint8_t* tile = smem + 256;
+  const int S = S_T > 0 ? S_T : S_rt;
+  const uint64_t tile_first = (uint64_t)blockIdx.x * PACK_TILE_LEAVES;
+  const uint32_t here = (uint32_t)min((uint64_t)PACK_TILE_LEAVES, n_leaves - tile_first);
+  stage_text_tile(lut, tile, body + tile_first * S, here * (uint32_t)S);
+#pragma unroll
+  for (int it = 0; it < PACK_LEAVES_PER_THREAD; ++it) {
+    const uint32_t j = it * PACK_THREADS + threadIdx.x;
+    if (j < here) {
+      uint32_t bad = 0xFFFFFFFFu;
+      const unsigned long long v = pack_leaf<S_T>(lut, tile, j, S, bad);
+      if (bad != 0xFFFFFFFFu) {
+        uint32_t c = tile[bad];
+        if (c >= 'a' && c <= 'z') c -= 32;
+        atomicMin(&flags->bad_symbol, ((tile_first * S + bad) << 8) | c);
+      }
+      insert_leaf<DIRECT>(v, S, (uint32_t)(tile_first + j), tab, tmp, flags);
+    }
+  }
+}
+
+// Leaves from a packed array (the std::vector<dna> constructor, shared_tree.cpp:212).
+template <bool DIRECT>
+__global__ void __launch_bounds__(LVL_THREADS)
+leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n, int S, LevelTable tab,
+                       uint32_t* __restrict__ tmp, BuildFlags* flags) {
+  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= n) return;
+  const unsigned long long v = __ldg(leaves + p);
+  if (v & ~leaf_mask(S)) flags->bad_leaf = 1u;
+  insert_leaf<DIRECT>(v, S, p, tab, tmp, flags);
+}
+
+// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
+__global__ void __launch_bounds__(LVL_THREADS)
+node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab,
+                   uint32_t* __restrict__ tmp) {
+  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= n_next) return;
+  uint32_t l, r;
+  if (2 * (uint64_t)p + 1 < n_cur) {
+    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
+    l = pr.x;
+    r = pr.y;
+  } else {  // odd tail: node{last, nullptr} (utility.h:17-29)
+    l = cur[2 * (uint64_t)p];
+    r = PTR_NULL;
+  }
+  uint32_t cl, cr, f;
+  canonical_node(l, r, cl, cr, f);
+  const unsigned long long key = ((unsigned long long)cl << 32) | cr;
+  const uint32_t s = table_insert(tab.slots, tab.cap, key, p);
+  tmp[p] = s | f;
+}
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(LVL_THREADS)
+count_first_kernel(const uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, uint32_t* __restrict__ bitmask,
+                   uint32_t* __restrict__ blockcnt) {
+  __shared__ uint32_t warp_cnt[LVL_THREADS / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    bool first = false;
+    if (p < n) {
+      const uint32_t s = tmp[p] & IDX_MASK;
+      const uint32_t mp = DIRECT ? __ldcg(tab.dminpos + s) : __ldcg(&tab.slots[s].minpos);
+      first = (mp == p);
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) {
+      bitmask[p >> 5] = word;
+      cnt += __popc(word);
+    }
+  }
+  if (lane == 0) warp_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < LVL_THREADS / 32; ++w) total += warp_cnt[w];
+    blockcnt[blockIdx.x] = total;
+  }
+}
+
+// In-place exclusive scan of the per-CTA counts (single CTA); total -> *total_out.
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ cnt, uint32_t nb,
+                                                           uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry_s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? cnt[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sum[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t before = carry + (warp ? warp_sum[warp - 1] : 0u) + x - v;
+    if (i < nb) cnt[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(LVL_THREADS)
+assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
+              const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S) {
+  __shared__ uint32_t word_pref[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t words[LVL_ITERS];
+#pragma unroll
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p0 = blockIdx.x * LVL_TILE + it * LVL_THREADS + warp * 32;
+    words[it] = p0 < n ? bitmask[p0 >> 5] : 0u;
+    if (lane == 0) word_pref[it * (LVL_THREADS / 32) + warp] = __popc(words[it]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = word_pref[lane];
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    word_pref[lane] = x - v;
+  }
+  __syncthreads();
+  const uint32_t base = blockbase[blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    if (p < n && ((words[it] >> lane) & 1u)) {
+      const uint32_t rank = base + word_pref[it * (LVL_THREADS / 32) + warp] + __popc(words[it] & ((1u << lane) - 1u));
+      const uint32_t t = tmp[p];
+      const uint32_t s = t & IDX_MASK;
+      if (MODE == MODE_LEAF_DIRECT) {
+        tab.dids[s] = rank;
+        reinterpret_cast<unsigned long long*>(uniq)[rank] = leaf_from_2bit(s, S);
+      } else {
+        const unsigned long long key = (MODE == MODE_LEAF_HASH && s == tab.cap) ? EMPTY_KEY : __ldcg(&tab.slots[s].key);
+        tab.slots[s].id = rank;
+        if (MODE == MODE_LEAF_HASH) reinterpret_cast<unsigned long long*>(uniq)[rank] = key;
+        else reinterpret_cast<uint2*>(uniq)[rank] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+      }
+      tmp[p] = finish_pointer(rank, t & ~IDX_MASK);
+    }
+  }
+}
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(LVL_THREADS)
+resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    if (p < n) {
+      const uint32_t word = bitmask[p >> 5];
+      if (!((word >> lane) & 1u)) {
+        const uint32_t t = tmp[p];
+        const uint32_t s = t & IDX_MASK;
+        const uint32_t id = DIRECT ? __ldcg(tab.dids + s) : __ldcg(&tab.slots[s].id);
+        tmp[p] = finish_pointer(id, t & ~IDX_MASK);
+      }
+    }
+  }
+}
+
+// ---- host orchestration -----------------------------------------------------------
+
+namespace {
+
+struct LeafInput {
+  const char* body = nullptr;                 // device, 16-byte aligned
+  const unsigned long long* leaves = nullptr; // device
+};
+
+struct Scratch {
+  DevBuf<uint32_t> ptr_a, ptr_b, bitmask, blockcnt, counts, dminpos, dids;
+  DevBuf<Slot> slots;
+  DevBuf<BuildFlags> flags;
+  DevBuf<uint32_t> root;
+};
+
+uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
+
+template <int S_T, bool DIRECT>
+void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags) {
+  const size_t smem = pack_smem_bytes(ctx.S);
+  Launch l(ctx, "leaf_insert");
+  leaf_insert_text_kernel<S_T, DIRECT><<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(
+      body, n, ctx.S, tab, tmp, flags);
+}
+
+// count -> scan -> assign -> resolve for one level whose inserts are already queued.
+template <int MODE>
+void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& sc, uint32_t* total_out, void* uniq) {
+  constexpr bool DIRECT = (MODE == MODE_LEAF_DIRECT);
+  const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
+  {
+    Launch l(ctx, "count_first");
+    count_first_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr);
+  }
+  {
+    Launch l(ctx, "scan_blocks");
+    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, total_out);
+  }
+  {
+    Launch l(ctx, "assign_ids");
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S);
+  }
+  {
+    Launch l(ctx, "resolve_ids");
+    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr);
+  }
+}
+
+int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
+  const int S = t.S;
+  cudaStream_t st = t.stream;
+  Scratch sc;
+  const uint64_t n1 = ceil_div(n0, 2);
+  STB_CUDA(t, sc.ptr_a.alloc(n0, st));
+  STB_CUDA(t, sc.ptr_b.alloc(n1, st));
+  STB_CUDA(t, sc.bitmask.alloc(ceil_div(n0, LVL_TILE) * (LVL_TILE / 32), st));
+  STB_CUDA(t, sc.blockcnt.alloc(ceil_div(n0, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.counts.alloc(80, st));
+  STB_CUDA(t, sc.flags.alloc(1, st));
+  STB_CUDA(t, sc.root.alloc(1, st));
+  {
+    BuildFlags init{~0ull, 0u, 0u};
+    STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+  }
+
+  // ---- leaf level ----
+  const uint64_t direct_entries = direct ? (1ull << (2 * S)) : 0;
+  const uint32_t leaf_cap = direct ? 0u : table_cap(n0);
+  const uint32_t node_cap_max = table_cap(n1);
+  STB_CUDA(t, sc.slots.alloc((uint64_t)std::max(leaf_cap, node_cap_max) + 1, st));
+  LevelTable tab{sc.slots.ptr, nullptr, nullptr, leaf_cap};
+  if (direct) {
+    STB_CUDA(t, sc.dminpos.alloc(direct_entries, st));
+    STB_CUDA(t, sc.dids.alloc(direct_entries, st));
+    tab.dminpos = sc.dminpos.ptr;
+    tab.dids = sc.dids.ptr;
+    Launch l(t, "table_clear", false);
+    STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
+  } else {
+    Launch l(t, "table_clear", false);
+    STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, ((uint64_t)leaf_cap + 1) * sizeof(Slot), st));
+  }
+  const uint64_t leaf_store = direct ? std::min<uint64_t>(n0, direct_entries) : n0;
+  STB_CUDA(t, t.leaves.alloc(leaf_store, st));
+
+  if (in.body) {
+    if (direct) {
+      if (S == 12) launch_leaf_text<12, true>(t, in.body, n0, tab, sc.ptr_a.ptr, sc.flags.ptr);
+      else launch_leaf_text<0, true>(t, in.body, n0, tab, sc.ptr_a.ptr, sc.flags.ptr);
+    } else {
+      if (S == 12) launch_leaf_text<12, false>(t, in.body, n0, tab, sc.ptr_a.ptr, sc.flags.ptr);
+      else launch_leaf_text<0, false>(t, in.body, n0, tab, sc.ptr_a.ptr, sc.flags.ptr);
+    }
+  } else {
+    Launch l(t, "leaf_insert");
+    const unsigned nb = (unsigned)ceil_div(n0, LVL_THREADS);
+    if (direct) leaf_insert_u64_kernel<true><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
+    else leaf_insert_u64_kernel<false><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
+  }
+  if (direct) finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, (uint32_t)n0, tab, sc, sc.counts.ptr, t.leaves.ptr);
+  else finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, (uint32_t)n0, tab, sc, sc.counts.ptr, t.leaves.ptr);
+
+  // ---- node levels ----
+  t.layers.clear();
+  uint32_t* cur = sc.ptr_a.ptr;
+  uint32_t* nxt = sc.ptr_b.ptr;
+  uint64_t n_cur = n0;
+  int level = 0;
+  do {
+    const uint64_t n_next = ceil_div(n_cur, 2);
+    t.layers.emplace_back();
+    Layer& layer = t.layers.back();
+    STB_CUDA(t, layer.nodes.alloc(n_next, st));
+    LevelTable nt{sc.slots.ptr, nullptr, nullptr, table_cap(n_next)};
+    {
+      Launch l(t, "table_clear", false);
+      STB_CUDA(t, cudaMemsetAsync(nt.slots, 0xff, ((uint64_t)nt.cap + 1) * sizeof(Slot), st));
+    }
+    {
+      Launch l(t, "node_insert");
+      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt);
+    }
+    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, sc.counts.ptr + 1 + level, layer.nodes.ptr);
+    std::swap(cur, nxt);
+    n_cur = n_next;
+    ++level;
+  } while (n_cur > 1);
+  // `cur` now holds the single root pointer.
+
+  std::vector<uint32_t> counts(level + 1);
+  BuildFlags flags{};
+  uint32_t root = PTR_NULL;
+  STB_CUDA(t, cudaMemcpyAsync(counts.data(), sc.counts.ptr, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(&flags, sc.flags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(&root, cur, 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  STB_CUDA(t, cudaGetLastError());
+
+  if (flags.bad_symbol != ~0ull) {
+    t.clear();
+    return t.fail(STB_ERR_UNKNOWN_SYMBOL, unknown_symbol_message((int)(flags.bad_symbol & 0xff)));
+  }
+  if (flags.bad_leaf) {
+    t.clear();
+    return t.fail(STB_ERR_BAD_LEAF, "packed leaf has bits set at or above 4*dna_size");
+  }
+  if (direct && flags.non_acgt) {
+    t.clear();
+    return -1;  // caller retries with the hash-table leaf level
+  }
+  for (uint32_t c : counts)
+    if (c >= IDX_MASK) {
+      t.clear();
+      return t.fail(STB_ERR_INDEX_CEILING, "a layer has 2^29-1 or more unique items; the pointer format cannot index it");
+    }
+
+  t.n_leaves = counts[0];
+  for (int k = 0; k < level; ++k) t.layers[k].count = counts[k + 1];
+  t.root = root;
+  t.width = n0;
+  t.built = true;
+  t.plan_valid = false;
+
+  // Give back over-provisioned storage (worst case was one item per position).
+  if (t.n_leaves * 2 < t.leaves.count) {
+    DevBuf<unsigned long long> exact;
+    STB_CUDA(t, exact.alloc(t.n_leaves, st));
+    STB_CUDA(t, cudaMemcpyAsync(exact.ptr, t.leaves.ptr, t.n_leaves * 8, cudaMemcpyDeviceToDevice, st));
+    t.leaves = std::move(exact);
+  }
+  for (auto& layer : t.layers) {
+    if (layer.count * 2 < layer.nodes.count) {
+      DevBuf<uint2> exact;
+      STB_CUDA(t, exact.alloc(layer.count, st));
+      STB_CUDA(t, cudaMemcpyAsync(exact.ptr, layer.nodes.ptr, layer.count * 8, cudaMemcpyDeviceToDevice, st));
+      layer.nodes = std::move(exact);
+    }
+  }
+  return STB_OK;
+}
+
+int build_dispatch(Tree& t, const LeafInput& in, uint64_t n0) {
+  if (n0 == 0) return t.fail(STB_ERR_EMPTY, "input holds fewer than dna_size bases");
+  if (n0 >= 0xffffffffull) return t.fail(STB_ERR_TOO_LARGE, "more than 2^32-2 leaf positions");
+  t.clear();
+  const bool try_direct = t.S <= 12;
+  if (try_direct) {
+    const int s = build_impl(t, in, n0, true);
+    if (s != -1) return s;
+  }
+  if (n0 > 480000000ull)
+    return t.fail(STB_ERR_TOO_LARGE, "hash-table leaf level supports at most 480M leaf positions in this version");
+  return build_impl(t, in, n0, false);
+}
+
+}  // namespace
+
+int build_from_body(Tree& t, const char* d_body, uint64_t body_len) {
+  LeafInput in;
+  in.body = d_body;
+  return build_dispatch(t, in, body_len / (uint64_t)t.S);
+}
+
+int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n) {
+  LeafInput in;
+  in.leaves = d_leaves;
+  return build_dispatch(t, in, n);
+}
+
+}  // namespace stb

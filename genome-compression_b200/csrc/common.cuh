@@ -1,0 +1,310 @@
+// common.cuh — device helpers and host context shared by every translation unit.
+//
+// Semantics follow SURVEY.md Appendix A (derived from, and verified against, the
+// reference: include/dna.h, src/dna.cpp, include/shared_tree.h,
+// src/shared_tree.cpp).  Nothing here is translated from the reference's code:
+// the reference loops over nucleotides and builds tuples; these are closed-form
+// bit manipulations on the raw 64-bit leaf / 32-bit pointer words.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/shared_tree_b200.h"
+
+namespace stb {
+
+// ---- raw pointer layout (reference include/shared_tree.h:73-76) -------------------
+constexpr uint32_t IDX_MASK = 0x1fffffffu;
+constexpr uint32_t MIRROR = 0x20000000u;
+constexpr uint32_t TRANSPOSE = 0x40000000u;
+constexpr uint32_t INVARIANT = 0x80000000u;
+constexpr uint32_t KEY31 = 0x7fffffffu;
+constexpr uint32_t PTR_NULL = 0x9fffffffu;
+constexpr unsigned long long EMPTY_KEY = 0xffffffffffffffffull;
+
+// pointer{index, m, t, inv} (reference src/shared_tree.cpp:86-87).  `flags` carries
+// m/t/inv already at bits 29/30/31; the mirror bit is dropped on invariant targets.
+__host__ __device__ __forceinline__ uint32_t finish_pointer(uint32_t index, uint32_t flags) {
+  const uint32_t inv = flags & INVARIANT;
+  const uint32_t m = (flags & MIRROR) & ~(inv >> 2);
+  return index | m | (flags & TRANSPOSE) | inv;
+}
+
+// pointer{p, m, t} (reference src/shared_tree.cpp:76-80); m, t in {0,1}.
+__host__ __device__ __forceinline__ uint32_t compose(uint32_t p, uint32_t m, uint32_t t) {
+  const uint32_t inv = p >> 31;
+  const uint32_t is_null = ((p & KEY31) == IDX_MASK) ? 1u : 0u;
+  const uint32_t nm = (m ^ ((p >> 29) & 1u)) & (inv ^ 1u);
+  const uint32_t nt = (t ^ ((p >> 30) & 1u)) & (is_null ^ 1u);
+  return (p & (IDX_MASK | INVARIANT)) | (nm << 29) | (nt << 30);
+}
+
+__host__ __device__ __forceinline__ bool ptr_is_null(uint32_t p) { return (p & KEY31) == IDX_MASK; }
+
+__host__ __device__ __forceinline__ unsigned long long pair_key(uint32_t l, uint32_t r) {
+  return ((unsigned long long)(l & KEY31) << 32) | (unsigned long long)(r & KEY31);
+}
+
+// node::canonical + emplace_node's invariant (reference include/shared_tree.h:115-126,
+// src/shared_tree.cpp:662-672).  Returns the canonical children; flags at bits 29..31.
+__host__ __device__ __forceinline__ void canonical_node(uint32_t l, uint32_t r, uint32_t& cl, uint32_t& cr,
+                                                        uint32_t& flags) {
+  const uint32_t lt = compose(l, 0, 1), rt = compose(r, 0, 1);
+  const uint32_t lm = compose(l, 1, 0), rm = compose(r, 1, 0);
+  const uint32_t li = compose(l, 1, 1), ri = compose(r, 1, 1);
+  unsigned long long best = pair_key(l, r);
+  cl = l;
+  cr = r;
+  flags = 0;
+  unsigned long long k = pair_key(lt, rt);  // (m,t) = (0,1)
+  if (k < best) { best = k; cl = lt; cr = rt; flags = TRANSPOSE; }
+  k = pair_key(rm, lm);                     // (1,0)
+  if (k < best) { best = k; cl = rm; cr = lm; flags = MIRROR; }
+  k = pair_key(ri, li);                     // (1,1)
+  if (k < best) { best = k; cl = ri; cr = li; flags = MIRROR | TRANSPOSE; }
+  if ((l & KEY31) == (rm & KEY31)) flags |= INVARIANT;
+}
+
+// ---- leaves (reference src/dna.cpp:104-143) -----------------------------------------
+__host__ __device__ __forceinline__ unsigned long long leaf_transposed(unsigned long long v) {
+  v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+  return v;
+}
+
+__host__ __device__ __forceinline__ unsigned long long bit_reverse64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  return __brevll(v);
+#else
+  v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+  v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+  v = ((v >> 4) & 0x0f0f0f0f0f0f0f0full) | ((v & 0x0f0f0f0f0f0f0f0full) << 4);
+  v = ((v >> 8) & 0x00ff00ff00ff00ffull) | ((v & 0x00ff00ff00ff00ffull) << 8);
+  v = ((v >> 16) & 0x0000ffff0000ffffull) | ((v & 0x0000ffff0000ffffull) << 16);
+  return (v >> 32) | (v << 32);
+#endif
+}
+
+// inverted = mirrored(transposed(x)): a full 64-bit reversal reverses both the nibble
+// order and the bits inside each nibble.
+__host__ __device__ __forceinline__ unsigned long long leaf_inverted(unsigned long long v, int S) {
+  return bit_reverse64(v) >> (64 - 4 * S);
+}
+__host__ __device__ __forceinline__ unsigned long long leaf_mirrored(unsigned long long v, int S) {
+  return leaf_transposed(leaf_inverted(v, S));
+}
+
+// dna::canonical: minimum over (value, mirror, transpose); flags at bits 29..31.
+__host__ __device__ __forceinline__ unsigned long long canonical_leaf(unsigned long long v, int S, uint32_t& flags) {
+  const unsigned long long t = leaf_transposed(v);
+  const unsigned long long i = leaf_inverted(v, S);
+  const unsigned long long m = leaf_transposed(i);
+  unsigned long long best = v;
+  flags = 0;
+  if (t < best) { best = t; flags = TRANSPOSE; }
+  if (m < best) { best = m; flags = MIRROR; }
+  if (i < best) { best = i; flags = MIRROR | TRANSPOSE; }
+  if (v == m) flags |= INVARIANT;
+  return best;
+}
+
+__host__ __device__ __forceinline__ unsigned long long leaf_mask(int S) {
+  return S >= 16 ? ~0ull : ((1ull << (4 * S)) - 1ull);
+}
+
+// True when every one of the S nibbles is A/C/G/T (one-hot).
+__host__ __device__ __forceinline__ bool leaf_is_acgt(unsigned long long v, int S) {
+  const unsigned long long ones = 0x1111111111111111ull;
+  const unsigned long long pop = (v & ones) + ((v >> 1) & ones) + ((v >> 2) & ones) + ((v >> 3) & ones);
+  return pop == (ones & leaf_mask(S));
+}
+
+// One-hot 4-bit codes (A1 C2 G4 T8) -> 2-bit codes (A0 C1 G2 T3), nucleotide i at bits 2i.
+// Order-isomorphic to the 4-bit form, so canonical(4-bit) maps to the same class.
+__host__ __device__ __forceinline__ uint32_t leaf_to_2bit(unsigned long long v) {
+  const unsigned long long ones = 0x1111111111111111ull;
+  const unsigned long long b = (v >> 1) & ones, c = (v >> 2) & ones, d = (v >> 3) & ones;
+  unsigned long long x = b | (c << 1) | d | (d << 1);
+  x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0full;
+  x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
+  x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
+  x = (x | (x >> 16)) & 0x00000000ffffffffull;
+  return (uint32_t)x;
+}
+
+__host__ __device__ __forceinline__ unsigned long long leaf_from_2bit(uint32_t code, int S) {
+  unsigned long long x = code;
+  x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+  x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+  x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  const unsigned long long ones = 0x1111111111111111ull;
+  const unsigned long long lo = x & ones, hi = (x >> 1) & ones;
+  const unsigned long long v = (~lo & ~hi & ones) | ((lo & ~hi) << 1) | ((~lo & hi) << 2) | ((lo & hi) << 3);
+  return v & leaf_mask(S);
+}
+
+// ---- hashing -----------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  return (uint32_t)(k >> 32);
+}
+
+// 16-byte open-addressing slot.  `key` is claimed with a 64-bit CAS; `minpos` is the
+// smallest level position that produced the key (atomicMin); `id` is its
+// first-occurrence rank, written once the level's scan is done.
+struct __align__(16) Slot {
+  unsigned long long key;
+  uint32_t minpos;
+  uint32_t id;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void load_slot(const Slot* s, unsigned long long& key, uint32_t& minpos, uint32_t& id) {
+  // two single-copy-atomic 64-bit elements, read at L2 (the point of coherence for the CAS)
+  unsigned long long a, b;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(s));
+  key = a;
+  minpos = (uint32_t)b;
+  id = (uint32_t)(b >> 32);
+}
+
+// Finds or claims the slot of `key` and lowers its min-position to `pos`.
+// Slot `cap` (one past the probed range) is reserved for the key that equals the
+// empty marker (only the 16-nucleotide leaf "----------------" can).
+__device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos) {
+  uint32_t s;
+  if (key == EMPTY_KEY) {
+    s = cap;
+    if (__ldcg(&tab[s].minpos) <= pos) return s;
+  } else {
+    s = __umulhi(hash64(key), cap);
+    for (;;) {
+      unsigned long long k;
+      uint32_t mp, id;
+      load_slot(tab + s, k, mp, id);
+      if (k == key) {
+        if (mp <= pos) return s;  // min-position only ever decreases
+        break;
+      }
+      if (k == EMPTY_KEY) {
+        const unsigned long long old = atomicCAS(&tab[s].key, EMPTY_KEY, key);
+        if (old == EMPTY_KEY || old == key) break;
+      }
+      if (++s == cap) s = 0;
+    }
+  }
+  atomicMin(&tab[s].minpos, pos);
+  return s;
+}
+#endif
+
+// ---- host context ------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  int S = 12;
+  cudaStream_t stream = nullptr;
+  mutable std::string error;
+  bool profiling = false;
+
+  struct Pending { const char* name; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+  struct Acc { double ms = 0; uint64_t launches = 0; };
+  std::map<std::string, Acc> acc;
+  std::vector<std::string> acc_order;
+
+  int fail(int status, const std::string& msg) const {
+    error = msg;
+    return status;
+  }
+  int fail_cuda(cudaError_t e, const char* what, const char* file, int line) const {
+    error = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + file + ":" + std::to_string(line) + " (" + what + ")";
+    return STB_ERR_CUDA;
+  }
+  cudaEvent_t get_event();
+  void flush_profile();  // synchronises and folds pending events into acc
+  ~Ctx();
+};
+
+extern uint64_t g_kernel_launches;
+
+// RAII timing scope around one kernel launch (or one memset / copy).
+struct Launch {
+  Ctx& ctx;
+  Ctx::Pending p{};
+  bool kernel;
+  Launch(Ctx& c, const char* name, bool is_kernel = true) : ctx(c), kernel(is_kernel) {
+    if (kernel) ++g_kernel_launches;
+    if (ctx.profiling) {
+      p.name = name;
+      p.a = ctx.get_event();
+      p.b = ctx.get_event();
+      cudaEventRecord(p.a, ctx.stream);
+    }
+  }
+  ~Launch() {
+    if (ctx.profiling) {
+      cudaEventRecord(p.b, ctx.stream);
+      ctx.pending.push_back(p);
+    }
+  }
+};
+
+#define STB_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) return (ctx).fail_cuda(e__, #expr, __FILE__, __LINE__);      \
+  } while (0)
+
+#define STB_TRY(expr)                 \
+  do {                                \
+    int s__ = (expr);                 \
+    if (s__ != STB_OK) return s__;    \
+  } while (0)
+
+// Stream-ordered device buffer.
+template <typename T>
+struct DevBuf {
+  T* ptr = nullptr;
+  uint64_t count = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      ptr = o.ptr; count = o.count; stream = o.stream;
+      o.ptr = nullptr; o.count = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  cudaError_t alloc(uint64_t n, cudaStream_t s) {
+    release();
+    stream = s;
+    count = n;
+    if (n == 0) n = 1;
+    return cudaMallocAsync((void**)&ptr, n * sizeof(T), s);
+  }
+  void release() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+    ptr = nullptr;
+    count = 0;
+  }
+  uint64_t bytes() const { return count * sizeof(T); }
+};
+
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+}  // namespace stb

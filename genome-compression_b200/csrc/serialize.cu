@@ -1,0 +1,318 @@
+// serialize.cu — the .dag byte stream (reference src/shared_tree.cpp:488-546).
+//
+// Layout (all integers big-endian, include/utility.h:178-184):
+//   pointer root | u64 leaf_count | leaf_count x ceil(S/2) bytes |
+//   per node layer bottom-up: u64 node_count | node_count x (pointer left, pointer right)
+// pointer = 1..4 bytes: segment(2) transpose(1) mirror(1) offset-high(4), then the
+// remaining offset bytes (src/shared_tree.cpp:25-67, :122-142).
+//
+// The reference writes one byte at a time through ostream::put.  Here a plan pass
+// sums the encoded length of every 1024-node tile, a scan turns the sums into byte
+// offsets, and the emit pass has each CTA encode its tile into shared memory and
+// store it as aligned words.  bytes() is the plan's grand total.
+#include <algorithm>
+#include <cstring>
+
+#include "staging.cuh"
+#include "tree.h"
+
+namespace stb {
+
+constexpr int SER_THREADS = 256;
+constexpr int SER_PER_THREAD = 4;
+constexpr int SER_TILE = SER_THREADS * SER_PER_THREAD;  // 1024 nodes or leaves per CTA
+
+// encoded length of a pointer: 1 + segment (src/shared_tree.cpp:44-49, :122-125)
+__host__ __device__ __forceinline__ uint32_t ptr_len(uint32_t raw) {
+  const uint32_t idx = raw & IDX_MASK;
+  return 1u + (idx >= 16u) + (idx >= 4112u) + (idx >= 1052688u);
+}
+
+// writes the 1..4 bytes of a pointer; returns the length
+__host__ __device__ __forceinline__ uint32_t ptr_encode(uint32_t raw, uint8_t* out) {
+  const uint32_t idx = raw & IDX_MASK;
+  uint32_t seg, off;
+  if (idx == IDX_MASK) { seg = 3; off = 0xfffffffu; }
+  else if (idx < 16u) { seg = 0; off = idx; }
+  else if (idx < 4112u) { seg = 1; off = idx - 16u; }
+  else if (idx < 1052688u) { seg = 2; off = idx - 4112u; }
+  else { seg = 3; off = idx - 1052688u; }
+  const uint32_t flags = ((raw >> 29) & 1u) << 4 | ((raw >> 30) & 1u) << 5 | seg << 6;
+  out[0] = (uint8_t)((off >> (8 * seg)) | flags);
+  for (uint32_t b = 1; b <= seg; ++b) out[b] = (uint8_t)(off >> (8 * (seg - b)));
+  return seg + 1;
+}
+
+__global__ void __launch_bounds__(SER_THREADS)
+node_tile_bytes_kernel(const uint2* __restrict__ nodes, uint32_t n, unsigned long long* __restrict__ tile_bytes) {
+  __shared__ uint32_t sm[8];
+  uint32_t mine = 0;
+  const uint32_t first = blockIdx.x * SER_TILE + threadIdx.x * SER_PER_THREAD;
+#pragma unroll
+  for (int j = 0; j < SER_PER_THREAD; ++j)
+    if (first + j < n) {
+      const uint2 nd = __ldg(nodes + first + j);
+      mine += ptr_len(nd.x) + ptr_len(nd.y);
+    }
+  uint32_t total;
+  block_exclusive_sum_256(mine, sm, &total);
+  if (threadIdx.x == 0) tile_bytes[blockIdx.x] = total;
+}
+
+// exclusive scan (single CTA) of 64-bit tile sizes, in place; total -> *total_out
+__global__ void __launch_bounds__(1024)
+scan_u64_kernel(unsigned long long* __restrict__ v, uint32_t n, unsigned long long* __restrict__ total_out) {
+  __shared__ unsigned long long warp_sum[32];
+  __shared__ unsigned long long carry_s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const unsigned long long x0 = i < n ? v[i] : 0ull;
+    unsigned long long x = x0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long before = carry_s + (warp ? warp_sum[warp - 1] : 0ull) + x - x0;
+    if (i < n) v[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + x0;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(SER_THREADS)
+emit_nodes_kernel(const uint2* __restrict__ nodes, uint32_t n, const unsigned long long* __restrict__ tile_off,
+                  uint8_t* __restrict__ out, unsigned long long layer_base) {
+  __shared__ uint32_t sm[8];
+  __shared__ __align__(16) uint8_t stage[SER_TILE * 8 + 16];
+  const unsigned long long dst = layer_base + tile_off[blockIdx.x];
+  const uint32_t shift = (uint32_t)(dst & 3ull);
+  uint2 nd[SER_PER_THREAD];
+  uint32_t mine = 0;
+  const uint32_t first = blockIdx.x * SER_TILE + threadIdx.x * SER_PER_THREAD;
+#pragma unroll
+  for (int j = 0; j < SER_PER_THREAD; ++j) {
+    nd[j] = make_uint2(0, 0);
+    if (first + j < n) {
+      nd[j] = __ldg(nodes + first + j);
+      mine += ptr_len(nd[j].x) + ptr_len(nd[j].y);
+    }
+  }
+  uint32_t total;
+  uint32_t o = shift + block_exclusive_sum_256(mine, sm, &total);
+#pragma unroll
+  for (int j = 0; j < SER_PER_THREAD; ++j)
+    if (first + j < n) {
+      o += ptr_encode(nd[j].x, stage + o);
+      o += ptr_encode(nd[j].y, stage + o);
+    }
+  __syncthreads();
+  copy_out_staged<SER_THREADS>(reinterpret_cast<char*>(out) + (dst - shift), stage, shift, total);
+}
+
+// leaves: low ceil(S/2) bytes of the word, most significant first (src/dna.cpp:149-151)
+__global__ void __launch_bounds__(SER_THREADS)
+emit_leaves_kernel(const unsigned long long* __restrict__ leaves, uint32_t n, int leaf_bytes, uint8_t* __restrict__ out,
+                   unsigned long long base) {
+  __shared__ __align__(16) uint8_t stage[SER_TILE * 8 + 16];
+  const uint32_t tile_first = blockIdx.x * SER_TILE;
+  const uint32_t here = min((uint32_t)SER_TILE, n - tile_first);
+  const unsigned long long dst = base + (unsigned long long)tile_first * leaf_bytes;
+  const uint32_t shift = (uint32_t)(dst & 3ull);
+#pragma unroll
+  for (int it = 0; it < SER_PER_THREAD; ++it) {
+    const uint32_t j = it * SER_THREADS + threadIdx.x;
+    if (j < here) {
+      const unsigned long long v = __ldg(leaves + tile_first + j);
+      uint8_t* o = stage + shift + j * leaf_bytes;
+      for (int b = 0; b < leaf_bytes; ++b) o[b] = (uint8_t)(v >> (8 * (leaf_bytes - 1 - b)));
+    }
+  }
+  __syncthreads();
+  copy_out_staged<SER_THREADS>(reinterpret_cast<char*>(out) + (dst - shift), stage, shift, here * leaf_bytes);
+}
+
+struct Header {
+  unsigned long long off, value;
+  uint32_t bytes, pad;
+};
+__global__ void emit_headers_kernel(const Header* __restrict__ h, uint32_t n, uint8_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Header hd = h[i];
+  for (uint32_t b = 0; b < hd.bytes; ++b) out[hd.off + b] = (uint8_t)(hd.value >> (8 * (hd.bytes - 1 - b)));
+}
+
+// ---- host --------------------------------------------------------------------------
+
+int stream_plan(Tree& t) {
+  if (!t.built) return t.fail(STB_ERR_NOT_BUILT, "tree is empty");
+  if (t.plan_valid) return STB_OK;
+  cudaStream_t st = t.stream;
+  const size_t L = t.layers.size();
+  t.layer_tile_off.clear();
+  t.layer_tile_off.resize(L);
+  DevBuf<unsigned long long> totals;
+  STB_CUDA(t, totals.alloc(L, st));
+  for (size_t k = 0; k < L; ++k) {
+    const uint32_t n = (uint32_t)t.layers[k].count;
+    const uint32_t tiles = (uint32_t)ceil_div(n, SER_TILE);
+    STB_CUDA(t, t.layer_tile_off[k].alloc(tiles, st));
+    {
+      Launch l(t, "node_tile_bytes");
+      node_tile_bytes_kernel<<<tiles, SER_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, t.layer_tile_off[k].ptr);
+    }
+    {
+      Launch l(t, "scan_tile_bytes");
+      scan_u64_kernel<<<1, 1024, 0, st>>>(t.layer_tile_off[k].ptr, tiles, totals.ptr + k);
+    }
+  }
+  std::vector<unsigned long long> h(L);
+  STB_CUDA(t, cudaMemcpyAsync(h.data(), totals.ptr, L * 8, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  STB_CUDA(t, cudaGetLastError());
+  t.layer_stream_bytes.assign(h.begin(), h.end());
+  uint64_t total = ptr_len(t.root) + 8 + t.n_leaves * (uint64_t)((t.S + 1) / 2);
+  for (size_t k = 0; k < L; ++k) total += 8 + t.layer_stream_bytes[k];
+  t.stream_bytes = total;
+  t.plan_valid = true;
+  return STB_OK;
+}
+
+int serialize_tree(Tree& t, uint8_t* d_out, uint64_t cap) {
+  STB_TRY(stream_plan(t));
+  if (cap < t.stream_bytes) return t.fail(STB_ERR_BUFFER_TOO_SMALL, "serialize: buffer smaller than bytes()");
+  for (const auto& layer : t.layers)
+    if (layer.count > 1052688ull + 0xfffffffull)
+      return t.fail(STB_ERR_INDEX_CEILING, "a layer is too large for the 28-bit pointer offset");
+  if (t.n_leaves > 1052688ull + 0xfffffffull)
+    return t.fail(STB_ERR_INDEX_CEILING, "leaf table is too large for the 28-bit pointer offset");
+  cudaStream_t st = t.stream;
+  const int leaf_bytes = (t.S + 1) / 2;
+  std::vector<Header> headers;
+  uint8_t rootb[4];
+  const uint32_t rlen = ptr_encode(t.root, rootb);
+  unsigned long long rootv = 0;
+  for (uint32_t b = 0; b < rlen; ++b) rootv = (rootv << 8) | rootb[b];
+  uint64_t off = 0;
+  headers.push_back(Header{off, rootv, rlen, 0});
+  off += rlen;
+  headers.push_back(Header{off, t.n_leaves, 8, 0});
+  off += 8;
+  const uint64_t leaves_base = off;
+  off += t.n_leaves * (uint64_t)leaf_bytes;
+  std::vector<uint64_t> layer_base(t.layers.size());
+  for (size_t k = 0; k < t.layers.size(); ++k) {
+    headers.push_back(Header{off, t.layers[k].count, 8, 0});
+    off += 8;
+    layer_base[k] = off;
+    off += t.layer_stream_bytes[k];
+  }
+  DevBuf<Header> d_headers;
+  STB_CUDA(t, d_headers.alloc(headers.size(), st));
+  STB_CUDA(t, cudaMemcpyAsync(d_headers.ptr, headers.data(), headers.size() * sizeof(Header), cudaMemcpyHostToDevice, st));
+  {
+    Launch l(t, "emit_headers");
+    emit_headers_kernel<<<(unsigned)ceil_div(headers.size(), 64), 64, 0, st>>>(d_headers.ptr, (uint32_t)headers.size(), d_out);
+  }
+  if (t.n_leaves) {
+    Launch l(t, "emit_leaves");
+    emit_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, SER_TILE), SER_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, leaf_bytes, d_out, leaves_base);
+  }
+  for (size_t k = 0; k < t.layers.size(); ++k) {
+    const uint32_t n = (uint32_t)t.layers[k].count;
+    Launch l(t, "emit_nodes");
+    emit_nodes_kernel<<<(unsigned)ceil_div(n, SER_TILE), SER_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, t.layer_tile_off[k].ptr, d_out, layer_base[k]);
+  }
+  STB_CUDA(t, cudaStreamSynchronize(st));  // headers vector must outlive the copy
+  STB_CUDA(t, cudaGetLastError());
+  return STB_OK;
+}
+
+// Host-side parse of the variable-length stream (inherently sequential: every
+// pointer's length is known only from its first byte), then one upload per layer.
+// shared_tree::deserialize, src/shared_tree.cpp:520-538; pointers come back with
+// invariant = false (:162).
+int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
+  static const uint32_t start[4] = {0u, 16u, 4112u, 1052688u};
+  t.clear();
+  uint64_t o = 0;
+  auto read_ptr = [&](uint32_t& raw) -> bool {
+    if (o >= len) return false;
+    const uint32_t b0 = in[o];
+    const uint32_t seg = (b0 >> 6) & 3u;
+    if (o + seg + 1 > len) return false;
+    uint32_t off = b0 & 0xfu;
+    for (uint32_t b = 1; b <= seg; ++b) off = (off << 8) | in[o + b];
+    o += seg + 1;
+    const uint32_t idx = (seg == 3 && off == 0xfffffffu) ? IDX_MASK : start[seg] + off;
+    raw = idx | (((b0 >> 4) & 1u) << 29) | (((b0 >> 5) & 1u) << 30);
+    return true;
+  };
+  auto read_u64 = [&](uint64_t& v) -> bool {
+    if (o + 8 > len) return false;
+    v = 0;
+    for (int b = 0; b < 8; ++b) v = (v << 8) | in[o + b];
+    o += 8;
+    return true;
+  };
+  uint32_t root;
+  uint64_t n_leaves;
+  if (!read_ptr(root) || !read_u64(n_leaves)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside the header");
+  const int leaf_bytes = (t.S + 1) / 2;
+  if (n_leaves > (len - o) / (uint64_t)leaf_bytes) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside the leaf table");
+  std::vector<unsigned long long> leaves(n_leaves);
+  for (uint64_t i = 0; i < n_leaves; ++i) {
+    unsigned long long v = 0;
+    for (int b = 0; b < leaf_bytes; ++b) v = (v << 8) | in[o++];
+    leaves[i] = v;
+  }
+  cudaStream_t st = t.stream;
+  STB_CUDA(t, t.leaves.alloc(n_leaves, st));
+  STB_CUDA(t, cudaMemcpyAsync(t.leaves.ptr, leaves.data(), n_leaves * 8, cudaMemcpyHostToDevice, st));
+  std::vector<std::vector<uint2>> host_layers;
+  while (o + 8 <= len) {  // layers until the stream ends (:528-530)
+    uint64_t count;
+    read_u64(count);
+    if (count > (len - o) / 2) return t.fail(STB_ERR_BAD_STREAM, "layer size exceeds the remaining stream");
+    host_layers.emplace_back(count);
+    for (uint64_t i = 0; i < count; ++i) {
+      uint2 nd;
+      if (!read_ptr(nd.x) || !read_ptr(nd.y)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
+      host_layers.back()[i] = nd;
+    }
+  }
+  if (host_layers.empty()) return t.fail(STB_ERR_BAD_STREAM, "stream holds no node layer");
+  for (auto& hl : host_layers) {
+    t.layers.emplace_back();
+    Layer& layer = t.layers.back();
+    layer.count = hl.size();
+    STB_CUDA(t, layer.nodes.alloc(hl.size(), st));
+    STB_CUDA(t, cudaMemcpyAsync(layer.nodes.ptr, hl.data(), hl.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+  }
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  t.n_leaves = n_leaves;
+  t.root = root;
+  t.built = true;
+  t.plan_valid = false;
+  return compute_width(t);
+}
+
+}  // namespace stb

@@ -1,0 +1,342 @@
+// sort.cu — frequency sort of every layer (shared_tree::sort_tree).
+//
+// Replaces histogram / sort_leaves / sort_nodes / invert_indices / reorder_layer /
+// rewire_nodes (reference src/shared_tree.cpp:316-326, :350-483).  The reference sorts
+// layer by layer in two std::async waves because each sort_nodes call rewrites two
+// layers in place.  Here the dependency is removed instead: every child layer's
+// histogram depends only on its parent's *contents* (not its order), so all new
+// positions are computed first from the untouched tree, and each layer is then
+// permuted and rewired exactly once, out of place:
+//
+//     new_nodes[k][ newpos[k+1][i] ] = rewire(nodes[k][i], newpos[k])
+//
+// new position = rank under (frequency desc, old index asc) = a stable LSD radix sort
+// of (maxf - freq) over only the digits maxf needs; the last pass scatters the rank
+// straight into newpos[].
+#include <algorithm>
+
+#include "tree.h"
+
+namespace stb {
+
+constexpr int HS_THREADS = 256;
+
+// freq[child index] += 1 for every non-null pointer of the parent layer.
+__global__ void __launch_bounds__(HS_THREADS)
+histogram_kernel(const uint2* __restrict__ nodes, uint32_t n, uint32_t* __restrict__ freq) {
+  const uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint2 nd = __ldg(nodes + i);
+  if (!ptr_is_null(nd.x)) atomicAdd(freq + (nd.x & IDX_MASK), 1u);
+  if (!ptr_is_null(nd.y)) atomicAdd(freq + (nd.y & IDX_MASK), 1u);
+}
+
+__global__ void __launch_bounds__(HS_THREADS)
+max_kernel(const uint32_t* __restrict__ freq, uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x; i < n; i += gridDim.x * HS_THREADS) m = max(m, freq[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ---- stable LSD radix sort, 8-bit digits -----------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_GROUPS = 16;                           // 32-item groups per warp
+constexpr int RS_TILE = RS_THREADS * RS_GROUPS;         // 4096 items per CTA
+constexpr int RS_WARP_ITEMS = 32 * RS_GROUPS;           // a warp owns 512 consecutive items
+
+__device__ __forceinline__ uint32_t rs_digit(uint32_t freq, uint32_t maxf, int shift) {
+  return ((maxf - freq) >> shift) & 0xffu;
+}
+
+// Per-CTA digit histogram, written digit-major: hist[d * nblocks + b].
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t maxf, int shift, uint32_t nblocks,
+                  uint32_t* __restrict__ hist) {
+  __shared__ uint32_t bins[256];
+  bins[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warp_base = blockIdx.x * RS_TILE + warp * RS_WARP_ITEMS;
+#pragma unroll 4
+  for (int g = 0; g < RS_GROUPS; ++g) {
+    const uint32_t i = warp_base + g * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t d = ok ? rs_digit(keys[i], maxf, shift) : 0x100u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (ok && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&bins[d], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblocks + blockIdx.x] = bins[threadIdx.x];
+}
+
+// One CTA per digit: exclusive scan of its row (in place) + row total.
+__global__ void __launch_bounds__(1024)
+radix_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ row_total) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry_s;
+  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nblocks; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? row[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t before = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - v;
+    if (i < nblocks) row[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_total[blockIdx.x] = carry_s;
+}
+
+// Scatter pass.  FIRST: values are the implicit identity.  LAST: instead of moving the
+// pair, publish the destination rank: newpos[value] = rank.
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t n,
+                     uint32_t maxf, int shift, uint32_t nblocks, const uint32_t* __restrict__ hist,
+                     const uint32_t* __restrict__ row_total, uint32_t* __restrict__ keys_out,
+                     uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t digit_base[256];            // global offset of (digit, this CTA)
+  __shared__ uint32_t warp_cnt[RS_WARPS][256];    // per-warp counts, then running offsets
+  __shared__ uint32_t scan_tmp[RS_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // exclusive scan of the 256 row totals (8 warps x 32 lanes)
+  {
+    const uint32_t v = row_total[threadIdx.x];
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) scan_tmp[warp] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += scan_tmp[w];
+    digit_base[threadIdx.x] = before + x - v + hist[threadIdx.x * nblocks + blockIdx.x];
+  }
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) warp_cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+
+  const uint32_t warp_first = blockIdx.x * RS_TILE + warp * RS_WARP_ITEMS;
+  uint32_t key[RS_GROUPS];
+  // pass 1: per-warp digit counts
+#pragma unroll
+  for (int g = 0; g < RS_GROUPS; ++g) {
+    const uint32_t i = warp_first + g * 32 + lane;
+    const bool ok = i < n;
+    key[g] = ok ? keys_in[i] : 0u;
+    const uint32_t d = ok ? rs_digit(key[g], maxf, shift) : 0x100u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (ok && lane == (uint32_t)(__ffs(peers) - 1)) warp_cnt[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive scan over the warps, offset by the CTA's global base
+  {
+    uint32_t run = digit_base[threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = warp_cnt[w][threadIdx.x];
+      warp_cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // pass 2: stable scatter
+#pragma unroll
+  for (int g = 0; g < RS_GROUPS; ++g) {
+    const uint32_t i = warp_first + g * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t d = ok ? rs_digit(key[g], maxf, shift) : 0x100u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t dst = 0;
+    if (ok) dst = warp_cnt[warp][d] + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+    if (ok && lane == (uint32_t)(__ffs(peers) - 1)) warp_cnt[warp][d] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      const uint32_t v = FIRST ? i : vals_in[i];
+      if (LAST) {
+        vals_out[v] = dst;  // newpos[old index] = rank
+      } else {
+        keys_out[dst] = key[g];
+        vals_out[dst] = v;
+      }
+    }
+  }
+}
+
+// new_nodes[dst_map ? dst_map[i] : i] = nodes[i] with child indices mapped through
+// child_map (identity when null).  Flags are kept; null stays null (shared_tree.cpp:383-403).
+__global__ void __launch_bounds__(HS_THREADS)
+permute_rewire_kernel(const uint2* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ child_map,
+                      const uint32_t* __restrict__ dst_map, uint2* __restrict__ out) {
+  const uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  uint2 nd = __ldg(nodes + i);
+  if (child_map) {
+    if (!ptr_is_null(nd.x)) nd.x = (nd.x & ~IDX_MASK) | __ldg(child_map + (nd.x & IDX_MASK));
+    if (!ptr_is_null(nd.y)) nd.y = (nd.y & ~IDX_MASK) | __ldg(child_map + (nd.y & IDX_MASK));
+  }
+  out[dst_map ? __ldg(dst_map + i) : i] = nd;
+}
+
+__global__ void __launch_bounds__(HS_THREADS)
+permute_leaves_kernel(const unsigned long long* __restrict__ leaves, uint32_t n, const uint32_t* __restrict__ dst_map,
+                      unsigned long long* __restrict__ out) {
+  const uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  out[__ldg(dst_map + i)] = __ldg(leaves + i);
+}
+
+__global__ void widen_kernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// ---- host --------------------------------------------------------------------------
+
+static uint64_t child_count(const Tree& t, uint64_t layer) { return layer == 0 ? t.n_leaves : t.layers[layer - 1].count; }
+
+int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq) {
+  Tree& ctx = const_cast<Tree&>(t);
+  const uint64_t n_child = child_count(t, layer);
+  STB_CUDA(ctx, freq.alloc(n_child, t.stream));
+  STB_CUDA(ctx, cudaMemsetAsync(freq.ptr, 0, std::max<uint64_t>(n_child, 1) * 4, t.stream));
+  const uint32_t n = (uint32_t)t.layers[layer].count;
+  Launch l(ctx, "histogram");
+  histogram_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, t.stream>>>(t.layers[layer].nodes.ptr, n, freq.ptr);
+  return STB_OK;
+}
+
+int histogram_u64(const Tree& t, uint64_t layer, unsigned long long* d_out) {
+  Tree& ctx = const_cast<Tree&>(t);
+  DevBuf<uint32_t> freq;
+  STB_TRY(histogram_layer(t, layer, freq));
+  const uint32_t n = (uint32_t)child_count(t, layer);
+  Launch l(ctx, "widen");
+  widen_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, t.stream>>>(freq.ptr, n, d_out);
+  return STB_OK;
+}
+
+int sort_tree(Tree& t) {
+  if (!t.built) return t.fail(STB_ERR_NOT_BUILT, "sort_tree on an empty tree");
+  cudaStream_t st = t.stream;
+  const size_t L = t.layers.size();
+  // child layer c (0 = leaves, c>0 = node layer c-1) is referenced from node layer c.
+  std::vector<DevBuf<uint32_t>> freq(L), newpos(L);
+  DevBuf<uint32_t> d_max;
+  STB_CUDA(t, d_max.alloc(L, st));
+  STB_CUDA(t, cudaMemsetAsync(d_max.ptr, 0, L * 4, st));
+  for (size_t c = 0; c < L; ++c) {
+    STB_TRY(histogram_layer(t, c, freq[c]));
+    const uint32_t n = (uint32_t)child_count(t, c);
+    Launch l(t, "freq_max");
+    const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(n, HS_THREADS), 1184);
+    max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c].ptr, n, d_max.ptr + c);
+  }
+  std::vector<uint32_t> maxf(L);
+  STB_CUDA(t, cudaMemcpyAsync(maxf.data(), d_max.ptr, L * 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaStreamSynchronize(st));
+
+  // ranks
+  std::vector<bool> permuted(L, false);
+  for (size_t c = 0; c < L; ++c) {
+    const uint32_t n = (uint32_t)child_count(t, c);
+    int passes = 0;
+    for (uint32_t span = maxf[c] ? maxf[c] - 1 : 0; span; span >>= 8) ++passes;  // keys are maxf - freq in [0, maxf-1]
+    if (passes == 0 || n < 2) continue;  // every frequency equal: stable sort = identity
+    permuted[c] = true;
+    STB_CUDA(t, newpos[c].alloc(n, st));
+    const uint32_t nblocks = (uint32_t)ceil_div(n, RS_TILE);
+    DevBuf<uint32_t> hist, row_total, keys_a, vals_a, keys_b, vals_b;
+    STB_CUDA(t, hist.alloc((uint64_t)256 * nblocks, st));
+    STB_CUDA(t, row_total.alloc(256, st));
+    if (passes > 1) {
+      STB_CUDA(t, keys_a.alloc(n, st));
+      STB_CUDA(t, vals_a.alloc(n, st));
+    }
+    if (passes > 2) {
+      STB_CUDA(t, keys_b.alloc(n, st));
+      STB_CUDA(t, vals_b.alloc(n, st));
+    }
+    const uint32_t* kin = freq[c].ptr;
+    const uint32_t* vin = nullptr;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = 8 * p;
+      const bool first = p == 0, last = p == passes - 1;
+      uint32_t* kout = last ? nullptr : ((p & 1) ? keys_b.ptr : keys_a.ptr);
+      uint32_t* vout = last ? newpos[c].ptr : ((p & 1) ? vals_b.ptr : vals_a.ptr);
+      {
+        Launch l(t, "radix_hist");
+        radix_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, maxf[c], shift, nblocks, hist.ptr);
+      }
+      {
+        Launch l(t, "radix_rowscan");
+        radix_rowscan_kernel<<<256, 1024, 0, st>>>(hist.ptr, nblocks, row_total.ptr);
+      }
+      {
+        Launch l(t, "radix_scatter");
+        if (first && last) radix_scatter_kernel<true, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
+        else if (first) radix_scatter_kernel<true, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
+        else if (last) radix_scatter_kernel<false, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
+        else radix_scatter_kernel<false, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
+      }
+      kin = kout;
+      vin = vout;
+    }
+  }
+
+  // apply: leaves, then every node layer (the top layer keeps its order, :455/:469)
+  if (permuted[0]) {
+    DevBuf<unsigned long long> moved;
+    STB_CUDA(t, moved.alloc(t.n_leaves, st));
+    Launch l(t, "permute_leaves");
+    permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0].ptr, moved.ptr);
+    t.leaves = std::move(moved);
+  }
+  for (size_t k = 0; k < L; ++k) {
+    const uint32_t* child_map = permuted[k] ? newpos[k].ptr : nullptr;
+    const uint32_t* dst_map = (k + 1 < L && permuted[k + 1]) ? newpos[k + 1].ptr : nullptr;
+    if (!child_map && !dst_map) continue;
+    const uint32_t n = (uint32_t)t.layers[k].count;
+    DevBuf<uint2> moved;
+    STB_CUDA(t, moved.alloc(n, st));
+    {
+      Launch l(t, "permute_rewire");
+      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved.ptr);
+    }
+    t.layers[k].nodes = std::move(moved);
+  }
+  t.plan_valid = false;
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  STB_CUDA(t, cudaGetLastError());
+  return STB_OK;
+}
+
+}  // namespace stb

@@ -1,0 +1,76 @@
+// tree.h — device-resident shared_tree and the internal entry points of each stage.
+#pragma once
+
+#include "common.cuh"
+
+namespace stb {
+
+// Mirrors the reference's private members (include/shared_tree.h:232-236):
+//   std::vector<std::vector<node>> nodes;  ->  layers[k].nodes (uint2 = left,right) in HBM
+//   std::vector<dna> leaves;               ->  leaves (uint64) in HBM
+//   pointer root;                          ->  root
+struct Layer {
+  DevBuf<uint2> nodes;
+  uint64_t count = 0;
+};
+
+struct Tree : Ctx {
+  bool built = false;
+  uint64_t n_leaves = 0;
+  DevBuf<unsigned long long> leaves;
+  std::vector<Layer> layers;
+  uint32_t root = PTR_NULL;
+  uint64_t width = 0;
+
+  // serialization plan cache (per-layer byte totals), invalidated by build / sort
+  bool plan_valid = false;
+  uint64_t stream_bytes = 0;
+  std::vector<uint64_t> layer_stream_bytes;
+  std::vector<DevBuf<unsigned long long>> layer_tile_off;  // per layer: byte offset of each 1024-node tile
+
+  void clear() {
+    built = false;
+    n_leaves = 0;
+    leaves.release();
+    layers.clear();
+    root = PTR_NULL;
+    width = 0;
+    plan_valid = false;
+    layer_tile_off.clear();
+  }
+};
+
+// ingest.cu ------------------------------------------------------------------------
+// FASTA text (device) -> bare body (device, newly allocated).  body_len excludes
+// nothing yet (tail truncation happens at packing).
+int fasta_extract_body(Ctx& ctx, const char* d_text, uint64_t len, DevBuf<char>& body, uint64_t* body_len);
+// bare body (device) -> packed leaves (device); error on unknown symbols.
+int pack_body(Ctx& ctx, const char* d_body, uint64_t n_leaves, unsigned long long* d_leaves);
+
+// build.cu -------------------------------------------------------------------------
+int build_from_body(Tree& t, const char* d_body, uint64_t body_len);
+int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n);
+
+// sort.cu --------------------------------------------------------------------------
+int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq);
+int histogram_u64(const Tree& t, uint64_t layer, unsigned long long* d_out);
+int sort_tree(Tree& t);
+
+// serialize.cu ---------------------------------------------------------------------
+int stream_plan(Tree& t);
+int serialize_tree(Tree& t, uint8_t* d_out, uint64_t cap);
+int deserialize_tree(Tree& t, const uint8_t* h_bytes, uint64_t len);
+
+// decode.cu ------------------------------------------------------------------------
+int compute_width(Tree& t);
+int decode_range(const Tree& t, uint64_t first, uint64_t count, unsigned long long* d_out, char* d_ascii);
+int random_access(const Tree& t, const unsigned long long* d_index, uint64_t q, unsigned long long* d_out);
+
+// synth.cu -------------------------------------------------------------------------
+int synth_genome(Ctx& ctx, char* d_out, uint64_t n_bases, uint64_t first, uint64_t count, uint64_t seed,
+                 uint32_t repeat_permille);
+
+// shared error word for unknown symbols: (byte offset << 8) | upper-cased byte
+std::string unknown_symbol_message(int upper_byte);
+
+}  // namespace stb

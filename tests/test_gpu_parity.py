@@ -1,0 +1,260 @@
+"""GPU: the CUDA path, called through the C ABI (ctypes), against the oracle and the
+golden values.  Bit-exact everywhere: integer / byte / index work only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import CORPUS_CASES, corpus_text
+
+pytestmark = pytest.mark.gpu
+
+
+def hexs(a):
+    return [f"{int(v):x}" for v in a]
+
+
+def compare_trees(got, want, what=""):
+    """got: genome_compression_b200.SharedTree, want: oracle tree. Reports the first differing table."""
+    assert got.depth() == want.depth(), what
+    assert got.leaf_count() == want.leaf_count(), what
+    assert got.layer_counts() == want.layer_counts(), what
+    assert np.array_equal(got.leaves(), want.leaves()), (what, "leaf table")
+    for k in range(got.depth() - 1):
+        a, b = got.layer(k), want.layer(k)
+        if not np.array_equal(a, b):
+            bad = np.nonzero((a != b).any(axis=1))[0][:5]
+            raise AssertionError(f"{what}: layer {k} differs at nodes {bad}: got {a[bad]}, want {b[bad]}")
+    assert got.root() == want.root(), what
+    assert got.width() == want.width(), what
+
+
+def full_check(stb, oracle, text_or_leaves, S, from_text=True, rec=None, what=""):
+    tree = stb.SharedTree(S)
+    if from_text:
+        leaves = oracle.fasta_to_leaves(text_or_leaves, S)
+        tree.build_from_fasta(text_or_leaves)
+    else:
+        leaves = np.asarray(text_or_leaves, dtype=np.uint64)
+        tree.build_from_leaves(leaves)
+    want = oracle.build(leaves, S)
+    compare_trees(tree, want, what + " pre-sort")
+    pre = tree.serialize()
+    assert pre == want.serialize(), what + " pre-sort stream"
+    for k in range(tree.depth() - 1):
+        assert np.array_equal(tree.histogram(k), want.histogram(k)), (what, "histogram", k)
+    assert np.array_equal(tree.decode(), leaves), what + " decode pre-sort"
+    tree.sort()
+    want.sort()
+    compare_trees(tree, want, what + " post-sort")
+    post = tree.serialize()
+    assert tree.bytes() == len(post) == want.bytes()
+    assert post == want.serialize(), what + " post-sort stream"
+    if rec is not None:
+        assert len(pre) == rec["pre_bytes"] and hashlib.sha256(pre).hexdigest() == rec["pre_sha256"]
+        assert len(post) == rec["post_bytes"] and hashlib.sha256(post).hexdigest() == rec["post_sha256"]
+        assert tree.layer_counts() == rec["layer_counts"] and tree.width() == rec["width"]
+    n = len(leaves)
+    assert np.array_equal(tree.decode(), leaves), what + " decode post-sort"
+    text = tree.decode_ascii()
+    assert text == b"".join(stb.leaf_to_str(v, S).encode() for v in leaves[:200]) + text[200 * S:]
+    assert len(text) == n * S
+    rng = np.random.default_rng(n)
+    idx = np.concatenate([rng.integers(0, n, min(4 * n, 5000)), [0, n - 1]]).astype(np.uint64)
+    assert np.array_equal(tree.random_access(idx), leaves[idx]), what + " random access"
+    # sub-range decode
+    for first, count in ((0, 1), (n - 1, 1), (n // 3, min(n - n // 3, 777)), (1, n - 1) if n > 1 else (0, 1)):
+        assert np.array_equal(tree.decode(first, count), leaves[first:first + count]), (what, first, count)
+    # deserialize round trip (invariant bits are not stored)
+    back = stb.SharedTree(S).deserialize(post)
+    assert back.width() == n and back.leaf_count() == tree.leaf_count()
+    assert back.serialize() == post
+    assert np.array_equal(back.decode(), leaves)
+    assert np.array_equal(back.random_access(idx), leaves[idx])
+    # copy (tests/test.cpp:275)
+    twin = tree.clone()
+    assert twin.serialize() == post
+    return tree
+
+
+@pytest.mark.parametrize("name,S", CORPUS_CASES)
+def test_corpus(stb, oracle, golden, name, S):
+    rec = golden["corpus"]["records"][f"{name}:{S}"]
+    full_check(stb, oracle, corpus_text(name), S, rec=rec, what=f"{name}:{S}")
+
+
+def test_small_vectors(stb, oracle, golden):
+    for name, rec in golden["small"].items():
+        S = rec["dna_size"]
+        leaves = np.array([int(x, 16) for x in rec["input_leaves"]], dtype=np.uint64)
+        tree = stb.SharedTree(S).build_from_leaves(leaves)
+        assert tree.serialize().hex() == rec["pre_hex"], name
+        assert hexs(tree.leaves()) == rec["stored_leaves"], name
+        for k, want in enumerate(rec["layers"]):
+            assert [f"{int(a):08x}" for a in tree.layer(k).reshape(-1)] == want, (name, k)
+            assert [int(c) for c in tree.histogram(k)] == rec["histograms"][k], (name, k)
+        tree.sort()
+        assert tree.serialize().hex() == rec["post_hex"], name
+        assert hexs(tree.decode()) == rec["input_leaves"], name
+        full_check(stb, oracle, leaves, S, from_text=False, what=name)
+
+
+def test_fasta_ingest(stb, oracle, golden):
+    for key, rec in golden["fasta"].items():
+        text = bytes.fromhex(rec["text_hex"])
+        S = rec["dna_size"]
+        got = stb.SharedTree(S).pack_fasta(text)
+        assert hexs(got) == rec["leaves"], key
+        if len(rec["leaves"]):
+            full_check(stb, oracle, text, S, what=key)
+
+
+def test_fasta_wrapped_large(stb, oracle):
+    # multi-record, 60-column wrapped, lower/upper case, IUPAC codes, crossing many 64 KiB tiles
+    rng = np.random.default_rng(3)
+    parts = []
+    for r in range(7):
+        n = int(rng.integers(50_000, 400_000))
+        seq = rng.choice(np.frombuffer(b"ACGTacgtNnRYKMSWBDHV-", dtype=np.uint8), size=n,
+                         p=[.2, .2, .2, .2, .04, .04, .04, .04] + [.04 / 13] * 13)
+        width = int(rng.choice([60, 70, 80, 61]))
+        lines = [seq[i:i + width].tobytes() for i in range(0, n, width)]
+        parts.append(b">record %d some description\n" % r + b"\n".join(lines) + b"\n")
+    text = b"".join(parts)
+    for S in (12, 7):
+        want = oracle.fasta_to_leaves(text, S)
+        got = stb.SharedTree(S).pack_fasta(text)
+        assert np.array_equal(got, want)
+    full_check(stb, oracle, text, 12, what="wrapped multi-record")
+
+
+def test_fasta_line_state_machine(stb, oracle):
+    # header/blank runs of every parity (src/fasta_reader.cpp:47-50): data lines that start
+    # with '>' are packed as data by the reference (and abort); blank ones vanish.
+    cases = [b">h\n\n\nACGTACGTACGTAAAA\n", b"\n\n\n\nACGTACGTACGTCCCC", b">a\n\n>b\nACGTACGTACGTGGGG\n\n\n>c\n\nTTTTACGTACGTGGGG",
+             b"ACGTAC\n\nGTACGT\n\n\nACGTACGTACGT\n"]
+    for text in cases:
+        want = oracle.fasta_to_leaves(text, 4)
+        got = stb.SharedTree(4).pack_fasta(text)
+        assert np.array_equal(got, want), text
+    with pytest.raises(stb.StbError) as e:
+        stb.SharedTree(4).pack_fasta(b">a\n>b\nACGTACGT\n")  # second header is read as data
+    assert e.value.name == "STB_ERR_UNKNOWN_SYMBOL" and "62" in str(e.value)
+
+
+def test_errors(stb):
+    t = stb.SharedTree(12)
+    with pytest.raises(stb.StbError) as e:
+        t.build_from_fasta(b"ACGTACGTACGTACGTACGTACGx")
+    assert e.value.name == "STB_ERR_UNKNOWN_SYMBOL"
+    assert str(e.value).endswith("Encountered unknown symbol: 88 (ASCII code 88)")
+    # invalid byte inside the dropped tail is never looked at (src/fasta_reader.cpp:59-61)
+    assert t.build_from_fasta(b"ACGTACGTACGTACx").width() == 1
+    with pytest.raises(stb.StbError) as e:
+        t.build_from_fasta(b"ACGTACGTACG\r\nACGTACGTACGTA")
+    assert "13" in str(e.value)
+    with pytest.raises(stb.StbError) as e:
+        t.build_from_fasta(b"ACGT")
+    assert e.value.name == "STB_ERR_EMPTY"
+    with pytest.raises(stb.StbError) as e:
+        stb.SharedTree(3).build_from_leaves(np.array([0x1111], dtype=np.uint64))
+    assert e.value.name == "STB_ERR_BAD_LEAF"
+    with pytest.raises(stb.StbError) as e:
+        stb.SharedTree(12).width()
+    assert e.value.name == "STB_ERR_NOT_BUILT"
+    t.build_from_fasta(b"ACGTACGTACGT" * 5)
+    with pytest.raises(stb.StbError) as e:
+        t.random_access(np.array([5], dtype=np.uint64))
+    assert e.value.name == "STB_ERR_OUT_OF_RANGE"
+    with pytest.raises(stb.StbError) as e:
+        stb.SharedTree(12).deserialize(t.serialize()[:9])
+    assert e.value.name == "STB_ERR_BAD_STREAM"
+
+
+def test_iupac_and_hash_leaf_path(stb, oracle):
+    rng = np.random.default_rng(11)
+    codes = np.array([1, 2, 4, 8, 3, 12, 7, 14, 0, 9, 5, 11, 13, 10, 6, 15], dtype=np.uint64)
+    for S, n in ((12, 20000), (16, 9000), (13, 5000), (1, 3000), (5, 40000)):
+        nib = codes[rng.integers(0, 16, size=(n, S))]
+        leaves = (nib << (4 * np.arange(S, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+        leaves[n // 2:n // 2 + n // 4] = leaves[:n // 4]
+        if S == 16:  # the leaf whose word equals the table's empty marker
+            leaves[[5, 77, 78, n - 1]] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        full_check(stb, oracle, leaves, S, from_text=False, what=f"iupac S={S}")
+
+
+def test_acgt_large_sizes(stb, oracle):
+    rng = np.random.default_rng(12)
+    for S in (14, 16, 9):  # ACGT-only but beyond / below the direct-table sizes
+        n = 30000
+        nib = np.array([1, 2, 4, 8], dtype=np.uint64)[rng.integers(0, 4, size=(n, S))]
+        leaves = (nib << (4 * np.arange(S, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+        leaves[n // 2:n // 2 + 4096] = leaves[:4096]
+        full_check(stb, oracle, leaves, S, from_text=False, what=f"acgt S={S}")
+
+
+def test_synthetic_matches_oracle_generator(stb, oracle):
+    import torch
+    n = 3_000_000
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(buf, n, seed=42, repeat_permille=500)
+    got = buf.cpu().numpy()
+    want = oracle.synth(n, 42, 500)
+    assert np.array_equal(got, want)
+    part = torch.empty(100_001, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(part, n, first=1_234_567, seed=42, repeat_permille=500)
+    assert np.array_equal(part.cpu().numpy(), want[1_234_567:1_234_567 + 100_001])
+    reps = oracle.synth_repeats(n, 42, 500)
+    covered = int(reps["len"].sum())
+    assert 0.35 * n < covered < 0.65 * n
+
+
+def test_synthetic_tree_parity(stb, oracle):
+    import torch
+    n = 6_000_000
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(buf, n, seed=7, repeat_permille=500)
+    text = buf.cpu().numpy().tobytes()
+    leaves = oracle.fasta_to_leaves(text, 12)
+    tree = stb.SharedTree(12).build_from_body(buf)
+    want = oracle.build(leaves, 12)
+    compare_trees(tree, want, "synthetic 6 Mbp")
+    tree.sort()
+    want.sort()
+    assert tree.serialize() == want.serialize()
+    assert tree.leaf_count() < tree.width() / 2  # planted repeats + 12-mer saturation dedup
+
+
+def test_large_properties(stb):
+    """Sizes the oracle would not finish quickly: size-independent properties only."""
+    import torch
+    n = 200_000_000
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(buf, n, seed=1, repeat_permille=500)
+    tree = stb.SharedTree(12).build_from_body(buf)
+    w = tree.width()
+    assert w == n // 12
+    counts = tree.layer_counts()
+    assert counts[-1] == 1 and len(counts) == int(np.ceil(np.log2(w)))
+    tree.sort()
+    out = torch.empty(w * 12, dtype=torch.uint8, device="cuda")
+    tree.decode_ascii(out=out)
+    assert torch.equal(out, buf[:w * 12])  # encode -> decode round trip
+    idx = torch.randint(0, w, (1_000_000,), device="cuda", dtype=torch.int64)
+    got = torch.empty(1_000_000, dtype=torch.int64, device="cuda")
+    tree.random_access(idx, out=got)
+    leaves = torch.empty(w, dtype=torch.int64, device="cuda")
+    tree.decode(out=leaves)
+    assert torch.equal(got, leaves[idx])
+    # stream round trip: serialize -> deserialize -> identical stream and content
+    stream = tree.serialize()
+    assert len(stream) == tree.bytes()
+    back = stb.SharedTree(12).deserialize(stream)
+    assert back.width() == w
+    out2 = torch.empty(w * 12, dtype=torch.uint8, device="cuda")
+    back.decode_ascii(out=out2)
+    assert torch.equal(out2, out)
+    assert hashlib.sha256(back.serialize()).digest() == hashlib.sha256(stream).digest()
+    # idempotence: sorting a sorted tree changes nothing
+    tree.sort()
+    assert hashlib.sha256(tree.serialize()).digest() == hashlib.sha256(stream).digest()
