@@ -13,9 +13,10 @@
 //     count    position p is a first occurrence iff minpos == p -> bitmask +
 //              per-CTA counts                                  [random read]
 //     scan     exclusive scan of the per-CTA counts           [tiny]
-//     assign   first occurrences get id = rank, publish it in the table, append
-//              the item to the layer in id order, emit their pointer
-//     resolve  the other positions fetch the id                [random read]
+//     assign   first occurrences get id = rank, append the item to the layer in id
+//              order and emit their pointer                    [coalesced]
+//     resolve  later occurrences read the id out of the first occurrence's
+//              finished pointer                                [random read]
 //
 // IDs are first-occurrence ranks in position order, independent of which thread won
 // which atomic, so the result equals the reference's sequential emplace order.
@@ -58,7 +59,7 @@ __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_
     s = leaf_to_2bit(canon);
     if (__ldcg(tab.dminpos + s) > pos) atomicMin(tab.dminpos + s, pos);
   } else {
-    s = table_insert(tab.slots, tab.cap, canon, pos);
+    s = table_insert<true>(tab.slots, tab.cap, canon, pos);
   }
   tmp[pos] = s | f;
 }
@@ -104,12 +105,14 @@ leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n
   insert_leaf<DIRECT>(v, S, p, tab, tmp, flags);
 }
 
-// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
+// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672), for the
+// positions [p_begin, p_end) of the level.
+template <bool PROBE_FIRST>
 __global__ void __launch_bounds__(LVL_THREADS)
-node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab,
+node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p_begin, uint32_t p_end, LevelTable tab,
                    uint32_t* __restrict__ tmp) {
-  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
-  if (p >= n_next) return;
+  const uint32_t p = p_begin + blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= p_end) return;
   uint32_t l, r;
   if (2 * (uint64_t)p + 1 < n_cur) {
     const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
@@ -122,25 +125,31 @@ node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
   uint32_t cl, cr, f;
   canonical_node(l, r, cl, cr, f);
   const unsigned long long key = ((unsigned long long)cl << 32) | cr;
-  const uint32_t s = table_insert(tab.slots, tab.cap, key, p);
+  const uint32_t s = table_insert<PROBE_FIRST>(tab.slots, tab.cap, key, p);
   tmp[p] = s | f;
 }
 
 template <bool DIRECT>
 __global__ void __launch_bounds__(LVL_THREADS)
-count_first_kernel(const uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, uint32_t* __restrict__ bitmask,
-                   uint32_t* __restrict__ blockcnt) {
+count_first_kernel(uint32_t* __restrict__ tmp, uint32_t n, uint32_t first_block, LevelTable tab,
+                   uint32_t* __restrict__ bitmask, uint32_t* __restrict__ blockcnt) {
   __shared__ uint32_t warp_cnt[LVL_THREADS / 32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t block = first_block + blockIdx.x;
   uint32_t cnt = 0;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
     bool first = false;
     if (p < n) {
-      const uint32_t s = tmp[p] & IDX_MASK;
+      const uint32_t t = tmp[p];
+      const uint32_t s = t & IDX_MASK;
       const uint32_t mp = DIRECT ? __ldcg(tab.dminpos + s) : __ldcg(&tab.slots[s].minpos);
       first = (mp == p);
+      // hash levels: a later occurrence only needs to know WHERE the first one is; its id is
+      // read from the first one's finished pointer (resolve_kernel), so ids are never
+      // scattered into the table.
+      if (!DIRECT && !first) tmp[p] = (t & ~IDX_MASK) | mp;
     }
     const uint32_t word = __ballot_sync(0xffffffffu, first);
     if (lane == 0) {
@@ -154,7 +163,7 @@ count_first_kernel(const uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab,
     uint32_t total = 0;
 #pragma unroll
     for (int w = 0; w < LVL_THREADS / 32; ++w) total += warp_cnt[w];
-    blockcnt[blockIdx.x] = total;
+    blockcnt[block] = total;
   }
 }
 
@@ -199,10 +208,14 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict_
 
 enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
 
+// First occurrences: id = rank in position order; append the item to its layer in id order
+// and emit the finished pointer.  Node items are recomputed from the child pointers
+// (coalesced) rather than fetched from the table (random).
 template <int MODE>
 __global__ void __launch_bounds__(LVL_THREADS)
 assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
-              const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S) {
+              const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S,
+              const uint32_t* __restrict__ children, uint32_t n_children) {
   __shared__ uint32_t word_pref[32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t words[LVL_ITERS];
@@ -235,17 +248,30 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
       if (MODE == MODE_LEAF_DIRECT) {
         tab.dids[s] = rank;
         reinterpret_cast<unsigned long long*>(uniq)[rank] = leaf_from_2bit(s, S);
+      } else if (MODE == MODE_LEAF_HASH) {
+        reinterpret_cast<unsigned long long*>(uniq)[rank] = (s == tab.cap) ? EMPTY_KEY : __ldcg(&tab.slots[s].key);
       } else {
-        const unsigned long long key = (MODE == MODE_LEAF_HASH && s == tab.cap) ? EMPTY_KEY : __ldcg(&tab.slots[s].key);
-        tab.slots[s].id = rank;
-        if (MODE == MODE_LEAF_HASH) reinterpret_cast<unsigned long long*>(uniq)[rank] = key;
-        else reinterpret_cast<uint2*>(uniq)[rank] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+        uint32_t l, r;
+        if (2 * (uint64_t)p + 1 < n_children) {
+          const uint2 pr = __ldg(reinterpret_cast<const uint2*>(children) + p);
+          l = pr.x;
+          r = pr.y;
+        } else {
+          l = children[2 * (uint64_t)p];
+          r = PTR_NULL;
+        }
+        uint32_t cl, cr, f;
+        canonical_node(l, r, cl, cr, f);
+        reinterpret_cast<uint2*>(uniq)[rank] = make_uint2(cl, cr);
       }
       tmp[p] = finish_pointer(rank, t & ~IDX_MASK);
     }
   }
 }
 
+// Later occurrences: direct mode looks the id up in the (L2-sized) id table; hash levels
+// read it from the finished pointer of the first occurrence, whose position count_first
+// left in tmp[p].
 template <bool DIRECT>
 __global__ void __launch_bounds__(LVL_THREADS)
 resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask) {
@@ -258,7 +284,7 @@ resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uin
       if (!((word >> lane) & 1u)) {
         const uint32_t t = tmp[p];
         const uint32_t s = t & IDX_MASK;
-        const uint32_t id = DIRECT ? __ldcg(tab.dids + s) : __ldcg(&tab.slots[s].id);
+        const uint32_t id = DIRECT ? __ldcg(tab.dids + s) : (__ldcg(tmp + s) & IDX_MASK);
         tmp[p] = finish_pointer(id, t & ~IDX_MASK);
       }
     }
@@ -293,12 +319,13 @@ void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, ui
 
 // count -> scan -> assign -> resolve for one level whose inserts are already queued.
 template <int MODE>
-void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& sc, uint32_t* total_out, void* uniq) {
+void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& sc, uint32_t* total_out, void* uniq,
+                  const uint32_t* children = nullptr, uint32_t n_children = 0) {
   constexpr bool DIRECT = (MODE == MODE_LEAF_DIRECT);
   const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
-  {
+  if (MODE != MODE_NODE) {  // node levels count chunk by chunk, right behind their inserts
     Launch l(ctx, "count_first");
-    count_first_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr);
+    count_first_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, 0u, tab, sc.bitmask.ptr, sc.blockcnt.ptr);
   }
   {
     Launch l(ctx, "scan_blocks");
@@ -306,7 +333,7 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
   }
   {
     Launch l(ctx, "assign_ids");
-    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S);
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children);
   }
   {
     Launch l(ctx, "resolve_ids");
@@ -385,10 +412,16 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
       STB_CUDA(t, cudaMemsetAsync(nt.slots, 0xff, ((uint64_t)nt.cap + 1) * sizeof(Slot), st));
     }
     {
+      // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
+      // and chunking insert+count to keep table lines in L2 did not pay (profiles/README.md).
       Launch l(t, "node_insert");
-      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt);
+      node_insert_kernel<true><<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, 0u, (uint32_t)n_next, nt, nxt);
     }
-    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, sc.counts.ptr + 1 + level, layer.nodes.ptr);
+    {
+      Launch l(t, "count_first");
+      count_first_kernel<false><<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(nxt, (uint32_t)n_next, 0u, nt, sc.bitmask.ptr, sc.blockcnt.ptr);
+    }
+    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, sc.counts.ptr + 1 + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
     std::swap(cur, nxt);
     n_cur = n_next;
     ++level;

@@ -158,28 +158,53 @@ __host__ __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
   return (uint32_t)(k >> 32);
 }
 
-// 16-byte open-addressing slot.  `key` is claimed with a 64-bit CAS; `minpos` is the
-// smallest level position that produced the key (atomicMin); `id` is its
-// first-occurrence rank, written once the level's scan is done.
+// 16-byte open-addressing slot, claimed whole by one 128-bit CAS.  `minpos` is the
+// smallest level position that produced the key (atomicMin afterwards).  The last word
+// is padding: ids are never stored in the table (see resolve_kernel).
 struct __align__(16) Slot {
   unsigned long long key;
   uint32_t minpos;
-  uint32_t id;
+  uint32_t pad;
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void load_slot(const Slot* s, unsigned long long& key, uint32_t& minpos, uint32_t& id) {
+__device__ __forceinline__ void load_slot(const Slot* s, unsigned long long& key, uint32_t& minpos) {
   // two single-copy-atomic 64-bit elements, read at L2 (the point of coherence for the CAS)
   unsigned long long a, b;
   asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(s));
   key = a;
   minpos = (uint32_t)b;
-  id = (uint32_t)(b >> 32);
+}
+
+// 128-bit compare-and-swap on a whole slot (sm_90+: atom.cas.b128).  Claims an empty
+// slot with key AND min-position in one L2 atomic; returns the previous contents.
+__device__ __forceinline__ void claim_slot(Slot* s, unsigned long long key, uint32_t pos, unsigned long long& old_key,
+                                           uint32_t& old_minpos) {
+  const unsigned long long empty = EMPTY_KEY;
+  const unsigned long long hi = 0xffffffff00000000ull | pos;
+  unsigned long long olo, ohi;
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 cmp, val, old;\n\t"
+      "mov.b128 cmp, {%2, %2};\n\t"
+      "mov.b128 val, {%3, %4};\n\t"
+      "atom.global.cas.b128 old, [%5], cmp, val;\n\t"
+      "mov.b128 {%0, %1}, old;\n\t"
+      "}"
+      : "=l"(olo), "=l"(ohi)
+      : "l"(empty), "l"(key), "l"(hi), "l"(s)
+      : "memory");
+  old_key = olo;
+  old_minpos = (uint32_t)ohi;
 }
 
 // Finds or claims the slot of `key` and lowers its min-position to `pos`.
+// PROBE_FIRST: read the slot before trying to claim it (levels where most positions
+// repeat an earlier key); otherwise claim optimistically (levels where most keys are
+// new: one atomic per position instead of load + CAS + min).
 // Slot `cap` (one past the probed range) is reserved for the key that equals the
 // empty marker (only the 16-nucleotide leaf "----------------" can).
+template <bool PROBE_FIRST>
 __device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos) {
   uint32_t s;
   if (key == EMPTY_KEY) {
@@ -189,15 +214,19 @@ __device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsign
     s = __umulhi(hash64(key), cap);
     for (;;) {
       unsigned long long k;
-      uint32_t mp, id;
-      load_slot(tab + s, k, mp, id);
+      uint32_t mp;
+      bool probed = false;
+      if (PROBE_FIRST) {
+        load_slot(tab + s, k, mp);
+        probed = (k != EMPTY_KEY);
+      }
+      if (!probed) {
+        claim_slot(tab + s, key, pos, k, mp);
+        if (k == EMPTY_KEY) return s;  // claimed: key and min-position written together
+      }
       if (k == key) {
         if (mp <= pos) return s;  // min-position only ever decreases
         break;
-      }
-      if (k == EMPTY_KEY) {
-        const unsigned long long old = atomicCAS(&tab[s].key, EMPTY_KEY, key);
-        if (old == EMPTY_KEY || old == key) break;
       }
       if (++s == cap) s = 0;
     }

@@ -222,7 +222,7 @@ def test_synthetic_tree_parity(stb, oracle):
     tree.sort()
     want.sort()
     assert tree.serialize() == want.serialize()
-    assert tree.leaf_count() < tree.width() / 2  # planted repeats + 12-mer saturation dedup
+    assert tree.leaf_count() < tree.width() and tree.layer_count(0) < tree.width() // 2  # planted repeats dedup
 
 
 def test_large_properties(stb):
