@@ -21,7 +21,7 @@ LIB = HERE / "libshared_tree_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
-HOST_BINARIES = {"compress_b200": ["compress.cpp"], "host_selftest": ["selftest.cpp"]}
+HOST_BINARIES = {"compress_b200": ["compress.cpp"]}
 
 
 def _sources():
@@ -81,10 +81,10 @@ def build_host(force: bool = False) -> None:
         if not all(p.exists() for p in paths):
             continue
         out = host / name
-        deps = paths + list(host.glob("*.h")) + [LIB]
+        deps = paths + list((host / "include").glob("*.h")) + [LIB, inc / "shared_tree_b200.h"]
         if force or _stale(out, deps):
-            cmd = ["g++", "-std=c++17", "-O2", "-Wall", f"-I{inc}", f"-I{host}", *map(str, paths), "-o", str(out),
-                   f"-L{HERE}", "-lshared_tree_b200", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN/..", "-pthread"]
+            cmd = ["g++", "-std=c++17", "-O2", "-Wall", f"-I{inc}", f"-I{host / 'include'}", *map(str, paths), "-o", str(out),
+                   f"-L{HERE}", "-lshared_tree_b200", "-Wl,-rpath,$ORIGIN/..", "-pthread"]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError(f"g++ failed for {name}:\n{res.stdout}\n{res.stderr}")

@@ -50,6 +50,14 @@ def build_ref(force: bool = False) -> Path | None:
     return REF_SO
 
 
+def build_dropin() -> bool:
+    """Compiles the reference's unmodified compress.cpp / tests/test.cpp against the shim."""
+    outs = [HERE / "_ref" / "ref_tests_on_b200", HERE / "_ref" / "ref_compress_on_b200"]
+    if (REFERENCE_ROOT / "tests" / "test.cpp").exists():
+        subprocess.run(["make", "-C", str(HERE), "dropin", f"REF={REFERENCE_ROOT}"], check=True, capture_output=True)
+    return all(o.exists() for o in outs)
+
+
 def have_ref() -> bool:
     return REF_SO.exists()
 
