@@ -86,6 +86,14 @@ def _load() -> C.CDLL:
         "stb_profile_reset": [vp],
         "stb_profile_read": [vp, P(cp), P(C.c_double), P(u64), u64, P(u64)],
         "stb_synth_genome": [i32, vp, vp, u64, u64, u64, u64, u32],
+        # include/shared_tree_b200_dist.h
+        "stb_dist_pack_body": [vp, vp, u64, vp],
+        "stb_dist_partition": [vp, i32, vp, u64, u64, i32, vp, vp, vp, vp],
+        "stb_dist_owner": [vp, vp, vp, u64, vp, u32, vp, vp],
+        "stb_dist_rank_index": [vp, vp, u64, vp, vp],
+        "stb_dist_finish": [vp, i32, vp, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp],
+        "stb_dist_upper_levels": [vp, vp, u64, i32],
+        "stb_assemble": [vp, vp, u64, u64, P(u64), P(vp), u32, u64],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -341,6 +341,43 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
   }
 }
 
+// Node levels from a pointer array down to a single root pointer.  Appends one layer per
+// level to t.layers; counts_dev[level] receives each layer's size; returns the buffer that
+// holds the root pointer in *root_buf.
+int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t n_cur, uint32_t* counts_dev, int* levels_out,
+                    uint32_t** root_buf) {
+  cudaStream_t st = t.stream;
+  int level = 0;
+  do {
+    const uint64_t n_next = ceil_div(n_cur, 2);
+    t.layers.emplace_back();
+    Layer& layer = t.layers.back();
+    STB_CUDA(t, layer.nodes.alloc(n_next, st));
+    LevelTable nt{sc.slots.ptr, nullptr, nullptr, table_cap(n_next)};
+    {
+      Launch l(t, "table_clear", false);
+      STB_CUDA(t, cudaMemsetAsync(nt.slots, 0xff, ((uint64_t)nt.cap + 1) * sizeof(Slot), st));
+    }
+    {
+      // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
+      // and chunking insert+count to keep table lines in L2 did not pay (profiles/README.md).
+      Launch l(t, "node_insert");
+      node_insert_kernel<true><<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, 0u, (uint32_t)n_next, nt, nxt);
+    }
+    {
+      Launch l(t, "count_first");
+      count_first_kernel<false><<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(nxt, (uint32_t)n_next, 0u, nt, sc.bitmask.ptr, sc.blockcnt.ptr);
+    }
+    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
+    std::swap(cur, nxt);
+    n_cur = n_next;
+    ++level;
+  } while (n_cur > 1);
+  *levels_out = level;
+  *root_buf = cur;
+  return STB_OK;
+}
+
 int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   const int S = t.S;
   cudaStream_t st = t.stream;
@@ -397,35 +434,9 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
 
   // ---- node levels ----
   t.layers.clear();
-  uint32_t* cur = sc.ptr_a.ptr;
-  uint32_t* nxt = sc.ptr_b.ptr;
-  uint64_t n_cur = n0;
   int level = 0;
-  do {
-    const uint64_t n_next = ceil_div(n_cur, 2);
-    t.layers.emplace_back();
-    Layer& layer = t.layers.back();
-    STB_CUDA(t, layer.nodes.alloc(n_next, st));
-    LevelTable nt{sc.slots.ptr, nullptr, nullptr, table_cap(n_next)};
-    {
-      Launch l(t, "table_clear", false);
-      STB_CUDA(t, cudaMemsetAsync(nt.slots, 0xff, ((uint64_t)nt.cap + 1) * sizeof(Slot), st));
-    }
-    {
-      // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
-      // and chunking insert+count to keep table lines in L2 did not pay (profiles/README.md).
-      Launch l(t, "node_insert");
-      node_insert_kernel<true><<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, 0u, (uint32_t)n_next, nt, nxt);
-    }
-    {
-      Launch l(t, "count_first");
-      count_first_kernel<false><<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(nxt, (uint32_t)n_next, 0u, nt, sc.bitmask.ptr, sc.blockcnt.ptr);
-    }
-    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, sc.counts.ptr + 1 + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
-    std::swap(cur, nxt);
-    n_cur = n_next;
-    ++level;
-  } while (n_cur > 1);
+  uint32_t* cur = nullptr;
+  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n0, sc.counts.ptr + 1, &level, &cur));
   // `cur` now holds the single root pointer.
 
   std::vector<uint32_t> counts(level + 1);
@@ -495,6 +506,44 @@ int build_dispatch(Tree& t, const LeafInput& in, uint64_t n0) {
 }
 
 }  // namespace
+
+// Small top of a sharded build: node layers only, from a gathered pointer array.
+int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_least_one) {
+  if (n == 0) return t.fail(STB_ERR_EMPTY, "no pointers");
+  if (n > 400000000ull) return t.fail(STB_ERR_TOO_LARGE, "upper levels: too many pointers");
+  t.clear();
+  cudaStream_t st = t.stream;
+  if (n == 1 && !at_least_one) {  // already the root
+    uint32_t root = PTR_NULL;
+    STB_CUDA(t, cudaMemcpyAsync(&root, d_ptrs, 4, cudaMemcpyDeviceToHost, st));
+    STB_CUDA(t, cudaStreamSynchronize(st));
+    t.root = root;
+    t.built = true;
+    return STB_OK;
+  }
+  Scratch sc;
+  const uint64_t n1 = ceil_div(n, 2);
+  STB_CUDA(t, sc.ptr_a.alloc(n, st));
+  STB_CUDA(t, sc.ptr_b.alloc(n1, st));
+  STB_CUDA(t, sc.bitmask.alloc(ceil_div(n1, LVL_TILE) * (LVL_TILE / 32), st));
+  STB_CUDA(t, sc.blockcnt.alloc(ceil_div(n1, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.counts.alloc(80, st));
+  STB_CUDA(t, sc.slots.alloc((uint64_t)table_cap(n1) + 1, st));
+  STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, d_ptrs, n * 4, cudaMemcpyDeviceToDevice, st));
+  int level = 0;
+  uint32_t* cur = nullptr;
+  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n, sc.counts.ptr, &level, &cur));
+  std::vector<uint32_t> counts(level);
+  uint32_t root = PTR_NULL;
+  STB_CUDA(t, cudaMemcpyAsync(counts.data(), sc.counts.ptr, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(&root, cur, 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  STB_CUDA(t, cudaGetLastError());
+  for (int k = 0; k < level; ++k) t.layers[k].count = counts[k];
+  t.root = root;
+  t.built = true;
+  return STB_OK;
+}
 
 int build_from_body(Tree& t, const char* d_body, uint64_t body_len) {
   LeafInput in;

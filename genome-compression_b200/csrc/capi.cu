@@ -5,8 +5,6 @@
 
 #include "tree.h"
 
-struct stb_tree : stb::Tree {};
-
 namespace stb {
 
 uint64_t g_kernel_launches = 0;

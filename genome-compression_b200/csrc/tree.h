@@ -50,6 +50,10 @@ int pack_body(Ctx& ctx, const char* d_body, uint64_t n_leaves, unsigned long lon
 // build.cu -------------------------------------------------------------------------
 int build_from_body(Tree& t, const char* d_body, uint64_t body_len);
 int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n);
+int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_least_one);
+
+// dist.cu --------------------------------------------------------------------------
+// (entry points are extern "C", see include/shared_tree_b200_dist.h)
 
 // sort.cu --------------------------------------------------------------------------
 int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq);
@@ -74,3 +78,6 @@ int synth_genome(Ctx& ctx, char* d_out, uint64_t n_bases, uint64_t first, uint64
 std::string unknown_symbol_message(int upper_byte);
 
 }  // namespace stb
+
+// the opaque handle of the C ABI
+struct stb_tree : stb::Tree {};

@@ -1,0 +1,345 @@
+"""Sharded multi-GPU shared_tree build (BASELINE.json config 4).
+
+One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the
+plumbing, the stage kernels of include/shared_tree_b200_dist.h are the work.  Protocol
+per level (leaves, then node layers bottom-up):
+
+    partition by hash owner -> all_to_all(keys, positions) -> owner dedups with min global
+    position, answers every record, marks first occurrences in a bitmap -> all_to_all(answers),
+    all_reduce(bitmap) -> rank index -> ids = rank of the first occurrence's bit
+
+so node ids are first-occurrence ranks in GLOBAL position order: identical to the single-GPU
+build and to the reference (src/shared_tree.cpp:630-637, :662-672).  Rank g owns a contiguous
+power-of-two aligned range of positions at every sharded level (the analogue of the
+reference's 2^22-leaf segments, include/shared_tree.h:305-316); when a level is small the
+pointer arrays are gathered and rank 0 finishes alone.
+
+`stages` abstracts the device work: `CudaStages` (this file) calls the C ABI; the CPU tests
+plug in a numpy twin (tests/dist_numpy_stages.py) to exercise this host logic under gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+LEAF, NODE = 0, 1
+
+
+def ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
+
+
+@dataclass
+class ShardPlan:
+    """Which positions of which level a rank owns."""
+    n_leaves: int
+    world: int
+    cut: int = 1 << 16  # a level with at most this many positions is finished on rank 0
+    shard: int = field(init=False)
+
+    def __post_init__(self):
+        per = max(1, ceil_div(self.n_leaves, self.world))
+        self.shard = 1 << (per - 1).bit_length()  # power of two >= per
+
+    def level_total(self, level: int) -> int:
+        """Positions at `level` (0 = leaves, k = node layer k-1)."""
+        return ceil_div(self.n_leaves, 1 << level)
+
+    def level_range(self, rank: int, level: int):
+        per = self.shard >> level
+        total = self.level_total(level)
+        return min(total, rank * per), min(total, (rank + 1) * per)
+
+    def sharded_levels(self) -> int:
+        """Number of levels (leaf level included) that run distributed."""
+        levels = 1
+        while (self.shard >> levels) >= 1 and self.level_total(levels) > self.cut and self.level_total(levels) > 1:
+            levels += 1
+        return levels
+
+
+@dataclass
+class LayerSlice:
+    base: int          # id of the first item
+    count: int
+    items: torch.Tensor  # int64[count] leaves or int32[count, 2] nodes
+
+
+@dataclass
+class DistTree:
+    """Result of a sharded build: every rank holds its id-range of each sharded layer;
+    rank 0 additionally holds the top layers."""
+    dna_size: int
+    width: int
+    leaves: LayerSlice
+    layers: list          # LayerSlice per sharded node layer
+    layer_totals: list    # global unique count per sharded layer (leaf level first)
+    upper: object         # rank 0: stages' upper-tree object, else None
+    root: int | None
+
+
+class CudaStages:
+    """Device work through the C ABI (include/shared_tree_b200_dist.h)."""
+
+    def __init__(self, pkg, dna_size: int, device: int, stream: int | None = None):
+        self.pkg = pkg
+        self.ctx = pkg.SharedTree(dna_size, device=device, stream=stream)
+        self.dna_size = dna_size
+        self.device = torch.device("cuda", device)
+        self.device_index = device
+        self.stream = stream
+
+    def _check(self, st):
+        self.ctx._check(st)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
+
+    def pack_body(self, body, n_leaves, leaves_out):
+        self._check(self.pkg.lib.stb_dist_pack_body(self.ctx._h, self._p(body), n_leaves, self._p(leaves_out)))
+
+    def partition(self, kind, items, n_items, gpos0, world, keys, gpos, meta, counts):
+        self._check(self.pkg.lib.stb_dist_partition(self.ctx._h, kind, self._p(items), n_items, gpos0, world, self._p(keys),
+                                                    self._p(gpos), self._p(meta), self._p(counts)))
+
+    def owner(self, keys, gpos, n, table, cap, answers, bitmap):
+        self._check(self.pkg.lib.stb_dist_owner(self.ctx._h, self._p(keys), self._p(gpos), n, self._p(table), cap,
+                                                self._p(answers), self._p(bitmap)))
+
+    def rank_index(self, bitmap, n_words, word_prefix, scratch):
+        self._check(self.pkg.lib.stb_dist_rank_index(self.ctx._h, self._p(bitmap), n_words, self._p(word_prefix), self._p(scratch)))
+
+    def finish(self, kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, answers, pointers, slice_out, base_count):
+        self._check(self.pkg.lib.stb_dist_finish(self.ctx._h, kind, self._p(items), n_items, gpos0, self._p(bitmap),
+                                                 self._p(word_prefix), n_level, self._p(meta), self._p(answers), self._p(pointers),
+                                                 self._p(slice_out), self._p(base_count)))
+
+    def upper_levels(self, pointers, n, leaf_pointers):
+        tree = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
+        tree._check(self.pkg.lib.stb_dist_upper_levels(tree._h, self._p(pointers), n, int(leaf_pointers)))
+        return tree
+
+    def upper_layers(self, upper):
+        """[(count, int32[count,2] device tensor)] of the top layers + root."""
+        out = []
+        for k in range(upper.depth() - 1):
+            cnt = upper.layer_count(k)
+            buf = torch.empty((cnt, 2), dtype=torch.int32, device=self.device)
+            upper._check(self.pkg.lib.stb_copy_layer(upper._h, k, C.c_void_p(buf.data_ptr()), cnt, self.pkg.DEVICE))
+            out.append(buf)
+        return out, upper.root()
+
+    def assemble(self, leaves, layers, root, width):
+        tree = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
+        counts = (C.c_uint64 * len(layers))(*[int(l.shape[0]) for l in layers])
+        ptrs = (C.c_void_p * len(layers))(*[l.data_ptr() if l.numel() else 0 for l in layers])
+        tree._check(self.pkg.lib.stb_assemble(tree._h, self._p(leaves), leaves.numel(), len(layers), counts, ptrs, root, width))
+        return tree
+
+    def table(self, cap):
+        return torch.empty((cap + 1) * 2, dtype=torch.int64, device=self.device)
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+class TorchComm:
+    """Collectives over a torch.distributed process group (NCCL on GPUs, gloo on CPUs)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def all_to_all(self, send, send_counts, recv_counts):
+        recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        if self.world == 1:
+            recv.copy_(send)
+        else:
+            dist.all_to_all_single(recv, send, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
+        return recv
+
+    def count_matrix(self, counts_dev):
+        if self.world == 1:
+            return [counts_dev.tolist()]
+        gathered = torch.empty(self.world * self.world, dtype=counts_dev.dtype, device=counts_dev.device)
+        dist.all_gather_into_tensor(gathered, counts_dev, group=self.group)
+        return gathered.view(self.world, self.world).tolist()
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_object(self, x):
+        if self.world == 1:
+            return [x]
+        out = [None] * self.world
+        dist.all_gather_object(out, x, group=self.group)
+        return out
+
+
+class ThreadComm:
+    """Virtual ranks as threads of ONE process sharing one GPU: the same exchanges done by
+    slicing each other's tensors.  Lets a single-GPU box run the multi-rank stage kernels
+    (tests/test_gpu_dist.py); never used for measurements."""
+
+    class Shared:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.box = [None] * world
+
+    def __init__(self, shared, rank):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+
+    def _exchange(self, item):
+        self.sh.box[self.rank] = item
+        self.sh.barrier.wait()
+        items = list(self.sh.box)
+        self.sh.barrier.wait()
+        return items
+
+    def all_to_all(self, send, send_counts, recv_counts):
+        items = self._exchange((send, list(send_counts)))
+        parts = []
+        for src, (t, counts) in enumerate(items):
+            off = sum(counts[:self.rank])
+            assert counts[self.rank] == recv_counts[src]
+            parts.append(t[off:off + counts[self.rank]])
+        out = torch.cat(parts) if parts else send[:0]
+        self.sh.barrier.wait()  # nobody frees a send buffer that is still being read
+        return out
+
+    def count_matrix(self, counts_dev):
+        return [c.tolist() for c in self._exchange(counts_dev)]
+
+    def all_reduce_sum(self, t):
+        items = self._exchange(t)
+        total = torch.stack(items).sum(dim=0, dtype=t.dtype)
+        self.sh.barrier.wait()
+        t.copy_(total)
+        self.sh.barrier.wait()
+
+    def all_gather_object(self, x):
+        return self._exchange(x)
+
+
+class DistBuilder:
+    def __init__(self, stages, comm=None, cut: int = 1 << 16):
+        self.st = stages
+        self.comm = comm or TorchComm()
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.device = stages.device
+        self.cut = cut
+        self.collectives = 0
+
+    # -- collectives ------------------------------------------------------------------
+    def _all_to_all(self, send, send_counts, recv_counts):
+        self.collectives += 1
+        return self.comm.all_to_all(send, send_counts, recv_counts)
+
+    def _count_matrix(self, counts_dev):
+        self.collectives += 1
+        return self.comm.count_matrix(counts_dev)
+
+    def _all_reduce_sum(self, t):
+        self.collectives += 1
+        self.comm.all_reduce_sum(t)
+
+    def _gather_rows(self, t, counts, dst=0):
+        """Variable-length gather in rank order to `dst` (others get an empty tensor)."""
+        send = [t.shape[0] if r == dst else 0 for r in range(self.world)]
+        recv = list(counts) if self.rank == dst else [0] * self.world
+        return self._all_to_all(t, send, recv)
+
+    # -- one level --------------------------------------------------------------------
+    def _level(self, kind, items, n_items, gpos0, n_level):
+        st, world, dev = self.st, self.world, self.device
+        n_pos = n_items if kind == LEAF else ceil_div(n_items, 2)
+        keys = torch.empty(n_pos, dtype=torch.int64, device=dev)
+        gpos = torch.empty(n_pos, dtype=torch.int32, device=dev)
+        meta = torch.empty(n_pos, dtype=torch.int32, device=dev)
+        counts = torch.zeros(world, dtype=torch.int32, device=dev)
+        st.partition(kind, items, n_items, gpos0, world, keys, gpos, meta, counts)
+        matrix = self._count_matrix(counts)
+        send_counts = matrix[self.rank]
+        recv_counts = [matrix[src][self.rank] for src in range(world)]
+        rkeys = self._all_to_all(keys, send_counts, recv_counts)
+        rgpos = self._all_to_all(gpos, send_counts, recv_counts)
+        m = rkeys.shape[0]
+        n_words = ceil_div(n_level, 32)
+        bitmap = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        answers = torch.empty(m, dtype=torch.int32, device=dev)
+        cap = max(1024, 2 * m)
+        table = st.table(cap)
+        st.owner(rkeys, rgpos, m, table, cap, answers, bitmap)
+        del table, rkeys, rgpos
+        back = self._all_to_all(answers, recv_counts, send_counts)
+        self._all_reduce_sum(bitmap)  # first-occurrence bits are disjoint across owners: sum == or
+        word_prefix = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(ceil_div(n_words, 1024) + 1, dtype=torch.int32, device=dev)
+        st.rank_index(bitmap, n_words, word_prefix, scratch)
+        pointers = torch.empty(n_pos, dtype=torch.int32, device=dev)
+        slice_out = torch.empty(n_pos if kind == LEAF else (n_pos, 2), dtype=torch.int64 if kind == LEAF else torch.int32, device=dev)
+        base_count = torch.zeros(2, dtype=torch.int32, device=dev)
+        st.finish(kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, back, pointers, slice_out, base_count)
+        total = word_prefix[n_words:n_words + 1]
+        base, count, total = [int(v) & 0xFFFFFFFF for v in torch.cat([base_count, total]).tolist()]
+        return pointers, LayerSlice(base, count, slice_out[:count]), total
+
+    # -- whole build ------------------------------------------------------------------
+    def build_from_leaves(self, local_leaves, n_leaves_total: int) -> DistTree:
+        """local_leaves: int64 device tensor with this rank's range of packed leaves
+        (ShardPlan.level_range(rank, 0))."""
+        plan = ShardPlan(n_leaves_total, self.world, self.cut)
+        lo, hi = plan.level_range(self.rank, 0)
+        assert local_leaves.numel() == hi - lo, (local_leaves.numel(), lo, hi)
+        totals, layers = [], []
+        pointers, leaves, total = self._level(LEAF, local_leaves, hi - lo, lo, plan.level_total(0))
+        totals.append(total)
+        n_sharded = plan.sharded_levels()
+        for level in range(1, n_sharded):
+            lo, hi = plan.level_range(self.rank, level)
+            prev_lo, prev_hi = plan.level_range(self.rank, level - 1)
+            assert hi - lo == ceil_div(prev_hi - prev_lo, 2)
+            pointers, sl, total = self._level(NODE, pointers, prev_hi - prev_lo, lo, plan.level_total(level))
+            layers.append(sl)
+            totals.append(total)
+        # gather the last sharded level's pointers on rank 0 and finish there
+        last = n_sharded - 1
+        per_rank = [plan.level_range(r, last)[1] - plan.level_range(r, last)[0] for r in range(self.world)]
+        gathered = self._gather_rows(pointers, per_rank, dst=0)
+        upper, root = None, None
+        if self.rank == 0:
+            upper = self.st.upper_levels(gathered, gathered.shape[0], leaf_pointers=(n_sharded == 1))
+            root = upper.root()
+        return DistTree(self.st.dna_size, n_leaves_total, leaves, layers, totals, upper, root)
+
+    def build_from_body(self, local_body, n_bases_total: int) -> DistTree:
+        """local_body: uint8 device tensor holding the bases of this rank's leaf range."""
+        S = self.st.dna_size
+        n_leaves_total = n_bases_total // S
+        plan = ShardPlan(n_leaves_total, self.world, self.cut)
+        lo, hi = plan.level_range(self.rank, 0)
+        leaves = torch.empty(hi - lo, dtype=torch.int64, device=self.device)
+        self.st.pack_body(local_body, hi - lo, leaves)
+        return self.build_from_leaves(leaves, n_leaves_total)
+
+    def gather(self, tree: DistTree):
+        """Collects every slice on rank 0 and assembles an ordinary SharedTree there
+        (None on the other ranks).  Untimed in bench.py: only needed to serialize / verify."""
+        def gather_slice(sl):
+            counts = self.comm.all_gather_object(sl.count)
+            return self._gather_rows(sl.items.contiguous(), counts, dst=0)
+
+        leaves = gather_slice(tree.leaves)
+        layers = [gather_slice(sl) for sl in tree.layers]
+        if self.rank != 0:
+            return None
+        top, root = self.st.upper_layers(tree.upper)
+        return self.st.assemble(leaves, layers + top, root, tree.width)

@@ -1,0 +1,85 @@
+/*
+ * shared_tree_b200_dist.h — stage entry points of the multi-GPU build (C ABI).
+ *
+ * The reference is a single process (no collectives).  The sharded build of
+ * BASELINE.json config 4 keeps its semantics exactly: node ids are first-occurrence ranks in
+ * GLOBAL position order.  One process per GPU; every rank owns a contiguous, power-of-two
+ * aligned range of leaf positions (the analogue of the reference's own 2^22 / 2^25-leaf
+ * segments, include/shared_tree.h:305-316, src/shared_tree.cpp:719-763).  Per level:
+ *
+ *   1. partition   each rank canonicalises its positions (dna::canonical / node::canonical)
+ *                  and splits (key, global position) records by hash owner          [stage]
+ *   2. exchange    all-to-all of the records (NCCL, done by the caller)
+ *   3. owner       the owner dedups its keys with min-position, answers every record with the
+ *                  global position of the key's first occurrence and marks that position in
+ *                  a bitmap over the level's global positions                        [stage]
+ *   4. exchange    all-to-all of the answers back; all-reduce (sum = or: bits are disjoint)
+ *                  of the bitmap
+ *   5. rank index  exclusive popcount prefix per bitmap word: id(q) = rank of bit q  [stage]
+ *   6. finish      first occurrences append their item to the rank's slice of the layer
+ *                  (ids [base, base+count)), every position gets pointer{id(q), flags} [stage]
+ *
+ * The collectives live in the caller (genome-compression_b200/dist.py uses
+ * torch.distributed); these stages only see device pointers.  All buffers are caller
+ * allocated; `ctx` is any handle from stb_create (device, stream, dna_size, error text).
+ */
+#ifndef SHARED_TREE_B200_DIST_H
+#define SHARED_TREE_B200_DIST_H
+
+#include "shared_tree_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* body (device ASCII, no header/newline) -> packed leaves (device). dna.cpp:79-84. */
+int stb_dist_pack_body(stb_tree* ctx, const char* body_dev, uint64_t n_leaves, uint64_t* leaves_dev);
+
+/* Stage 1.  kind 0: items are packed leaves (uint64[n_items]); kind 1: items are the child
+ * pointer array (uint32[n_items]) and positions are pairs of children (odd tail -> null).
+ * n_positions = n_items (kind 0) or ceil(n_items/2) (kind 1).  Outputs, in owner order
+ * (owner 0's records first, stable within an owner): keys[n_positions], gpos[n_positions]
+ * (= gpos0 + local position), meta[n_positions] (= local position | flags << 29),
+ * counts[world] (records per owner). */
+int stb_dist_partition(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0, int world,
+                       uint64_t* keys_dev, uint32_t* gpos_dev, uint32_t* meta_dev, uint32_t* counts_dev);
+
+/* Stage 3.  table_dev: (cap + 1) * 16 bytes, cap >= 2 * n_records (cleared here);
+ * answers_dev[n_records] = global position of the first occurrence of the record's key;
+ * bitmap_dev (caller-zeroed, ceil(n_level_positions/32) words): bit q set for every first
+ * occurrence q owned here. */
+int stb_dist_owner(stb_tree* ctx, const uint64_t* keys_dev, const uint32_t* gpos_dev, uint64_t n_records, void* table_dev,
+                   uint32_t cap, uint32_t* answers_dev, uint32_t* bitmap_dev);
+
+/* Stage 5.  word_prefix_dev[n_words + 1]: exclusive popcount prefix (last entry = total);
+ * scratch_dev: ceil(n_words/1024) + 1 words. */
+int stb_dist_rank_index(stb_tree* ctx, const uint32_t* bitmap_dev, uint64_t n_words, uint32_t* word_prefix_dev,
+                        uint32_t* scratch_dev);
+
+/* Stage 6.  Same kind / items / gpos0 as stage 1.  answers_dev / meta_dev are in the
+ * rank's SEND order (what stage 1 produced, answers as returned by the exchange).
+ * Outputs: pointers_dev[n_positions]; layer_slice_dev: the items first seen in this rank's
+ * range, in id order (uint64 leaves or uint2 nodes), capacity n_positions;
+ * base_count_dev[2] = {first id of the slice, number of items}. */
+int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                    const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                    const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                    uint32_t* base_count_dev);
+
+/* Remaining (small) levels on one rank: builds node layers from a pointer array until one
+ * pointer is left.  The handle afterwards holds ONLY those layers (stb_layer_count,
+ * stb_copy_layer, stb_root work; leaf_count is 0).  leaf_pointers != 0: the array is the leaf
+ * level itself, so at least one node layer is built even for a single pointer (a lone leaf is
+ * wrapped as node{leaf, null}, include/shared_tree.h:282-299). */
+int stb_dist_upper_levels(stb_tree* tree, const uint32_t* pointers_dev, uint64_t n_pointers, int leaf_pointers);
+
+/* Assembles a complete tree from device arrays (copies them): the gathered result of a
+ * sharded build, or any externally produced tree.  layer_counts[n_layers],
+ * layers_dev[n_layers] (uint2 nodes each). */
+int stb_assemble(stb_tree* tree, const uint64_t* leaves_dev, uint64_t n_leaves, uint64_t n_layers,
+                 const uint64_t* layer_counts, const void* const* layers_dev, uint32_t root, uint64_t width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

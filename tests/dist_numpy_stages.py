@@ -1,0 +1,165 @@
+"""TEST-ONLY numpy twin of the multi-GPU stage kernels (include/shared_tree_b200_dist.h),
+built on the oracle's primitives.  It lets the host-side orchestration in
+genome-compression_b200/dist.py (shard plan, splits, collectives, level loop, gather) run
+under gloo on CPUs.  The product never imports this."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+IDX = 0x1FFFFFFF
+NULL = 0x9FFFFFFF
+
+
+def _u32(t):
+    return t.numpy().view(np.uint32)
+
+
+def _flags(f):  # oracle: bit0 mirror, bit1 transpose, bit2 invariant -> bits 29..31
+    return ((f & 1) << 29) | (((f >> 1) & 1) << 30) | (((f >> 2) & 1) << 31)
+
+
+def _finish(idx, flags):
+    if flags & 0x80000000:
+        flags &= ~0x20000000
+    return (idx | flags) & 0xFFFFFFFF
+
+
+class _Upper:
+    def __init__(self, layers, root):
+        self.layers, self._root = layers, root
+
+    def root(self):
+        return self._root
+
+
+class _Assembled:
+    def __init__(self, leaves, layers, root, width):
+        self.leaves_, self.layers_, self.root_, self.width_ = leaves, layers, root, width
+
+
+class NumpyStages:
+    def __init__(self, oracle, dna_size):
+        self.o = oracle
+        self.dna_size = dna_size
+        self.device = torch.device("cpu")
+
+    # (key, flags) of every local position
+    def _produce(self, kind, items, n_items):
+        if kind == 0:
+            vals = items.numpy().view(np.uint64)[:n_items]
+            out = [self.o.leaf_canonical(int(v), self.dna_size) for v in vals]
+            return [(c, _flags(f)) for c, f in out]
+        cur = _u32(items)[:n_items]
+        res = []
+        for i in range((n_items + 1) // 2):
+            l = int(cur[2 * i])
+            r = int(cur[2 * i + 1]) if 2 * i + 1 < n_items else NULL
+            cl, cr, f = self.o.node_canonical(l, r)
+            res.append(((cl << 32) | cr, _flags(f)))
+        return res
+
+    @staticmethod
+    def _owner(key, world):
+        return ((key * 0x9E3779B97F4A7C15) >> 40) % world
+
+    def pack_body(self, body, n_leaves, leaves_out):
+        text = body.numpy().tobytes()
+        S = self.dna_size
+        for i in range(n_leaves):
+            v, bad = self.o.pack(text[i * S:(i + 1) * S], S)
+            assert bad < 0
+            leaves_out.numpy().view(np.uint64)[i] = v
+
+    def partition(self, kind, items, n_items, gpos0, world, keys, gpos, meta, counts):
+        recs = self._produce(kind, items, n_items)
+        order = sorted(range(len(recs)), key=lambda i: self._owner(recs[i][0], world))  # stable
+        k, g, m = keys.numpy().view(np.uint64), _u32(gpos), _u32(meta)
+        c = np.zeros(world, dtype=np.int32)
+        for dst, i in enumerate(order):
+            k[dst] = recs[i][0]
+            g[dst] = gpos0 + i
+            m[dst] = i | recs[i][1]
+            c[self._owner(recs[i][0], world)] += 1
+        counts.numpy()[:] = c
+
+    def table(self, cap):
+        return torch.empty(0, dtype=torch.int64)
+
+    def owner(self, keys, gpos, n, table, cap, answers, bitmap):
+        k, g = keys.numpy().view(np.uint64)[:n], _u32(gpos)[:n]
+        first = {}
+        for key, pos in zip(k.tolist(), g.tolist()):
+            if key not in first or pos < first[key]:
+                first[key] = pos
+        a, b = _u32(answers), _u32(bitmap)
+        for j, (key, pos) in enumerate(zip(k.tolist(), g.tolist())):
+            q = first[key]
+            a[j] = q
+            if q == pos:
+                b[q >> 5] |= np.uint32(1 << (q & 31))
+
+    def rank_index(self, bitmap, n_words, word_prefix, scratch):
+        pop = np.array([bin(int(w)).count("1") for w in _u32(bitmap)[:n_words]], dtype=np.uint64)
+        wp = _u32(word_prefix)
+        wp[0] = 0
+        if n_words:
+            wp[1:n_words + 1] = np.cumsum(pop).astype(np.uint32)
+
+    def finish(self, kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, answers, pointers, slice_out, base_count):
+        b, wp = _u32(bitmap), _u32(word_prefix)
+        n_words = (n_level + 31) // 32
+
+        def rank(q):
+            if q >= n_level:
+                return int(wp[n_words])
+            return int(wp[q >> 5]) + bin(int(b[q >> 5]) & ((1 << (q & 31)) - 1)).count("1")
+
+        recs = self._produce(kind, items, n_items)
+        n_pos = len(recs)
+        base = rank(gpos0)
+        bc = _u32(base_count)
+        bc[0], bc[1] = base, rank(gpos0 + n_pos) - base
+        ptr = _u32(pointers)
+        for i, (key, f) in enumerate(recs):
+            g = gpos0 + i
+            if (int(b[g >> 5]) >> (g & 31)) & 1:
+                ident = rank(g)
+                if kind == 0:
+                    slice_out.numpy().view(np.uint64)[ident - base] = key
+                else:
+                    s = _u32(slice_out)
+                    s[ident - base, 0], s[ident - base, 1] = key >> 32, key & 0xFFFFFFFF
+                ptr[i] = _finish(ident, f)
+        m, a = _u32(meta), _u32(answers)
+        for j in range(n_pos):
+            pos, q = int(m[j]) & IDX, int(a[j])
+            if q != gpos0 + pos:
+                ptr[pos] = _finish(rank(q), int(m[j]) & ~IDX & 0xFFFFFFFF)
+
+    def upper_levels(self, pointers, n, leaf_pointers):
+        cur = [int(x) for x in _u32(pointers)[:n]]
+        layers = []
+        while len(cur) > 1 or (leaf_pointers and not layers):
+            ids, nodes, nxt = {}, [], []
+            for i in range((len(cur) + 1) // 2):
+                l = cur[2 * i]
+                r = cur[2 * i + 1] if 2 * i + 1 < len(cur) else NULL
+                cl, cr, f = self.o.node_canonical(l, r)
+                key = (cl << 32) | cr
+                if key not in ids:
+                    ids[key] = len(nodes)
+                    nodes.append((cl, cr))
+                nxt.append(_finish(ids[key], _flags(f)))
+            layers.append(np.array(nodes, dtype=np.uint32).reshape(-1, 2))
+            cur = nxt
+        return _Upper(layers, cur[0])
+
+    def upper_layers(self, upper):
+        return [torch.from_numpy(l.view(np.int32).copy()) for l in upper.layers], upper.root()
+
+    def assemble(self, leaves, layers, root, width):
+        return _Assembled(leaves.numpy().view(np.uint64).copy(), [_u32(l).reshape(-1, 2).copy() for l in layers], root, width)
+
+    def sync(self):
+        pass

@@ -6,7 +6,7 @@ from conftest import ROOT
 
 
 def declared_symbols():
-    text = (ROOT / "include" / "shared_tree_b200.h").read_text()
+    text = (ROOT / "include" / "shared_tree_b200.h").read_text() + (ROOT / "include" / "shared_tree_b200_dist.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(stb_[a-z0-9_]+)\s*\(", text)))
 

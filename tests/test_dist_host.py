@@ -1,0 +1,128 @@
+"""CPU: the multi-GPU host logic (genome-compression_b200/dist.py) under gloo, world sizes 1-3,
+with the numpy stage twin, checked against the oracle's single-process tree."""
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_package
+
+
+def make_leaves(n, S, seed):
+    rng = np.random.default_rng(seed)
+    codes = np.array([1, 2, 4, 8], dtype=np.uint64)
+    nib = codes[rng.integers(0, 2 if n < 64 else 4, size=(n, S))]
+    leaves = (nib << (4 * np.arange(S, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+    if n >= 16:  # planted repeat + a reverse-complement-ish mirror block
+        leaves[n // 2:n // 2 + n // 4] = leaves[:n // 4]
+    return leaves
+
+
+def _worker(rank, world, port, n, S, cut, seed, result_path):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pkg = load_package()
+        from dist_numpy_stages import NumpyStages
+        from oracle.pyoracle import Oracle
+        from genome_compression_b200.dist import DistBuilder, ShardPlan
+
+        oracle = Oracle()
+        leaves = make_leaves(n, S, seed)
+        plan = ShardPlan(n, world, cut)
+        lo, hi = plan.level_range(rank, 0)
+        local = torch.from_numpy(leaves[lo:hi].view(np.int64).copy())
+        builder = DistBuilder(NumpyStages(oracle, S), cut=cut)
+        tree = builder.build_from_leaves(local, n)
+        full = builder.gather(tree)
+        if rank == 0:
+            want = oracle.build(leaves, S)
+            assert len(full.layers_) == want.depth() - 1, (len(full.layers_), want.depth() - 1)
+            assert np.array_equal(full.leaves_, want.leaves())
+            for k, layer in enumerate(full.layers_):
+                assert np.array_equal(layer, want.layer(k)), k
+            assert full.root_ == want.root()
+            assert tree.layer_totals[0] == want.leaf_count()
+            for k, total in enumerate(tree.layer_totals[1:]):
+                assert total == want.layer_count(k)
+            with open(result_path, "w") as f:
+                f.write(f"ok {builder.collectives}")
+    finally:
+        dist.destroy_process_group()
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,n,S,cut", [(2, 1000, 12, 16), (2, 37, 12, 1), (3, 515, 5, 8), (2, 1, 12, 1), (2, 2, 12, 1), (1, 300, 12, 4)])
+def test_sharded_build_equals_oracle(world, n, S, cut):
+    with tempfile.TemporaryDirectory() as d:
+        result = os.path.join(d, "result")
+        mp.spawn(_worker, args=(world, free_port(), n, S, cut, 1234 + n, result), nprocs=world, join=True)
+        assert open(result).read().startswith("ok")
+
+
+def test_shard_plan():
+    load_package()
+    from genome_compression_b200.dist import ShardPlan
+    plan = ShardPlan(258_333_333, 8)
+    assert plan.shard == 1 << 25
+    assert plan.level_range(7, 0) == (7 << 25, 258_333_333)
+    for level in range(plan.sharded_levels()):
+        covered = 0
+        for r in range(8):
+            lo, hi = plan.level_range(r, level)
+            assert lo == covered or hi == lo
+            covered = max(covered, hi)
+            if level:
+                plo, phi = plan.level_range(r, level - 1)
+                assert hi - lo == -(-(phi - plo) // 2)
+        assert covered == plan.level_total(level)
+    assert plan.level_total(plan.sharded_levels() - 1) > plan.cut >= plan.level_total(plan.sharded_levels())
+    tiny = ShardPlan(1, 4, cut=1)
+    assert tiny.sharded_levels() == 1 and tiny.level_range(0, 0) == (0, 1) and tiny.level_range(3, 0) == (1, 1)
+
+
+def test_thread_comm_virtual_ranks(oracle):
+    """The in-process communicator used on single-GPU boxes, here with the numpy stages."""
+    import threading
+    load_package()
+    sys.path.insert(0, str(ROOT / "tests"))
+    from dist_numpy_stages import NumpyStages
+    from genome_compression_b200.dist import DistBuilder, ShardPlan, ThreadComm
+
+    n, S, world, cut = 700, 12, 4, 8
+    leaves = make_leaves(n, S, 77)
+    shared = ThreadComm.Shared(world)
+    plan = ShardPlan(n, world, cut)
+    out, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            lo, hi = plan.level_range(rank, 0)
+            builder = DistBuilder(NumpyStages(oracle, S), comm=ThreadComm(shared, rank), cut=cut)
+            out[rank] = builder.gather(builder.build_from_leaves(torch.from_numpy(leaves[lo:hi].view(np.int64).copy()), n))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            shared.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    want = oracle.build(leaves, S)
+    assert np.array_equal(out[0].leaves_, want.leaves())
+    assert all(np.array_equal(a, want.layer(k)) for k, a in enumerate(out[0].layers_))
+    assert out[0].root_ == want.root()
