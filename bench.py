@@ -202,7 +202,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        raise SystemExit("multi-GPU sharded build: see bench_multi (not wired in this revision)")
+        return run_b200_dist(args, world, rank, local_rank)
     torch.cuda.set_device(local_rank)
     pkg = load_package()
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -307,6 +307,113 @@ def run_b200(args):
         "tree": {"width": n0, "leaves": tree.leaf_count(), "nodes": tree.node_count(), "depth": tree.depth()},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_b200_dist(args, world, rank, local_rank):
+    """N > 1: the sharded build (genome-compression_b200/dist.py).  Strong scaling: the same
+    3.1 Gbp sequence split over the ranks by leaf range; per level one hash-owner all-to-all
+    and one bitmap all-reduce over NVLink (NCCL)."""
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = load_package()
+    from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peak_gbs, peak_src = 6650.0, "fallback"
+    if peaks_path.exists():
+        peak_gbs, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
+    n_bases = args.bases
+    n_leaves = n_bases // DNA
+    plan = ShardPlan(n_leaves, world)
+    lo, hi = plan.level_range(rank, 0)
+    stream = torch.cuda.current_stream()
+    body = torch.empty(max(16, (hi - lo) * DNA), dtype=torch.uint8, device="cuda")
+    if hi > lo:
+        pkg.synth_genome(body, n_bases, first=lo * DNA, count=(hi - lo) * DNA, seed=args.seed,
+                         repeat_permille=args.repeat_permille, device=local_rank, stream=stream.cuda_stream)
+    stages = CudaStages(pkg, DNA, local_rank, stream=stream.cuda_stream)
+    builder = DistBuilder(stages)
+    tree = None
+    for _ in range(args.warmup):
+        tree = builder.build_from_body(body, n_bases)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = pkg.kernel_launches()
+    stages.ctx.profile(True)
+    stages.ctx.profile_reset()
+    builder.collectives = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        tree = builder.build_from_body(body, n_bases)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([pkg.kernel_launches() - launches0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    prof = stages.ctx.profile_read()
+    stages.ctx.profile(False)
+    ms_per_step = float(ms.item()) / args.steps
+    bases_used = n_leaves * DNA
+    value = bases_used / (ms_per_step * 1e-3) / 1e9
+
+    # end to end: every rank's text shard starts in pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(body.numel(), dtype=torch.uint8, pin_memory=True)
+        host.copy_(body)
+        staging = torch.empty_like(body)
+        torch.cuda.synchronize()
+        dist.barrier()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            staging.copy_(host, non_blocking=True)
+            t = builder.build_from_body(staging, n_bases)
+            _ = (t.layer_totals, t.root)
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": bases_used / float(dt.item()) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": n_bases,
+               "d2h_bytes_per_step": 12 * len(tree.layer_totals) * world + 4, "ms_per_step": float(dt.item()) * 1e3, "steps": reps}
+
+    if rank == 0:
+        kernels = {name: {"ms_per_step": round(rec["ms"] / args.steps, 4), "launches_per_step": rec["launches"] // args.steps}
+                   for name, rec in prof.items()}
+        # algorithmic bytes of rank 0's share of the two table kernels
+        positions = sum(plan.level_range(0, lv)[1] - plan.level_range(0, lv)[0] for lv in range(plan.sharded_levels()))
+        dom = max((k for k in kernels if k.startswith("dist_")), key=lambda k: kernels[k]["ms_per_step"])
+        alg = {"dist_owner_insert": 12 * positions, "dist_owner_answer": 12 * positions, "dist_partition_hist": 8 * positions,
+               "dist_partition_scatter": 24 * positions, "dist_finish_first": 20 * positions, "dist_finish_rest": 12 * positions}.get(dom, 12 * positions)
+        ach = alg / (kernels[dom]["ms_per_step"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": workload_config(args, {"sharding": f"{world} ranks x {plan.shard} leaf positions, hash-owner all-to-all + bitmap "
+                                                         f"all-reduce per level, {plan.sharded_levels()} sharded levels, rest on rank 0"}),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
+                         "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
+                         "note": "rank 0's launches of the dominant stage kernel; algorithmic bytes = its record streams"},
+            "cpu_baseline": None, "kernels": kernels, "collectives_per_step": builder.collectives // args.steps,
+            "tree": {"width": n_leaves, "leaves": tree.layer_totals[0], "sharded_layer_nodes": tree.layer_totals[1:]},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

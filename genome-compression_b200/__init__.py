@@ -93,6 +93,8 @@ def _load() -> C.CDLL:
         "stb_dist_rank_index": [vp, vp, u64, vp, vp],
         "stb_dist_finish": [vp, i32, vp, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp],
         "stb_dist_upper_levels": [vp, vp, u64, i32],
+        "stb_dist_leaf_direct_minpos": [vp, vp, u64, u64, vp, vp, P(i32)],
+        "stb_dist_leaf_direct_finish": [vp, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp],
         "stb_assemble": [vp, vp, u64, u64, P(u64), P(vp), u32, u64],
     }
     for name, args in sig.items():

@@ -46,14 +46,14 @@ struct BuildFlags {
 
 template <bool DIRECT>
 __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_t pos, const LevelTable& tab,
-                                            uint32_t* __restrict__ tmp, BuildFlags* flags) {
+                                            uint32_t* __restrict__ tmp_at_pos, BuildFlags* flags) {
   uint32_t f;
   const unsigned long long canon = canonical_leaf(v, S, f);
   uint32_t s;
   if (DIRECT) {
     if (!leaf_is_acgt(v, S)) {
       flags->non_acgt = 1u;
-      tmp[pos] = 0u;
+      *tmp_at_pos = 0u;
       return;
     }
     s = leaf_to_2bit(canon);
@@ -61,7 +61,7 @@ __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_
   } else {
     s = table_insert<true>(tab.slots, tab.cap, canon, pos);
   }
-  tmp[pos] = s | f;
+  *tmp_at_pos = s | f;
 }
 
 // Leaves straight from the ASCII body: pack (dna.cpp:79-84) + canonical (dna.cpp:135)
@@ -69,7 +69,7 @@ __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_
 template <int S_T, bool DIRECT>
 __global__ void __launch_bounds__(PACK_THREADS)
 leaf_insert_text_kernel(const char* __restrict__ body, uint64_t n_leaves, int S_rt, LevelTable tab,
-                        uint32_t* __restrict__ tmp, BuildFlags* flags) {
+                        uint32_t* __restrict__ tmp, BuildFlags* flags, uint32_t pos0) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* lut = smem;
   uint8_t* tile = smem + 256;
@@ -88,7 +88,7 @@ leaf_insert_text_kernel(const char* __restrict__ body, uint64_t n_leaves, int S_
         if (c >= 'a' && c <= 'z') c -= 32;
         atomicMin(&flags->bad_symbol, ((tile_first * S + bad) << 8) | c);
       }
-      insert_leaf<DIRECT>(v, S, (uint32_t)(tile_first + j), tab, tmp, flags);
+      insert_leaf<DIRECT>(v, S, pos0 + (uint32_t)(tile_first + j), tab, tmp + tile_first + j, flags);
     }
   }
 }
@@ -102,7 +102,7 @@ leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n
   if (p >= n) return;
   const unsigned long long v = __ldg(leaves + p);
   if (v & ~leaf_mask(S)) flags->bad_leaf = 1u;
-  insert_leaf<DIRECT>(v, S, p, tab, tmp, flags);
+  insert_leaf<DIRECT>(v, S, p, tab, tmp + p, flags);
 }
 
 // One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672), for the
@@ -310,11 +310,11 @@ struct Scratch {
 uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
 
 template <int S_T, bool DIRECT>
-void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags) {
+void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags, uint32_t pos0 = 0) {
   const size_t smem = pack_smem_bytes(ctx.S);
   Launch l(ctx, "leaf_insert");
   leaf_insert_text_kernel<S_T, DIRECT><<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(
-      body, n, ctx.S, tab, tmp, flags);
+      body, n, ctx.S, tab, tmp, flags, pos0);
 }
 
 // count -> scan -> assign -> resolve for one level whose inserts are already queued.
@@ -542,6 +542,28 @@ int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_leas
   for (int k = 0; k < level; ++k) t.layers[k].count = counts[k];
   t.root = root;
   t.built = true;
+  return STB_OK;
+}
+
+// ---- multi-GPU leaf level on the direct-addressed table (dist.cu drives it) ---------------
+// Step 1: this rank's leaves lower the replicated table with GLOBAL positions.
+int dist_leaf_direct_minpos(Ctx& ctx, const char* d_body, uint64_t n_local, uint64_t gpos0, uint32_t* dminpos, uint32_t* tmp,
+                            int* non_acgt) {
+  *non_acgt = 0;
+  if (n_local == 0) return STB_OK;
+  DevBuf<BuildFlags> flags;
+  STB_CUDA(ctx, flags.alloc(1, ctx.stream));
+  BuildFlags init{~0ull, 0u, 0u};
+  STB_CUDA(ctx, cudaMemcpyAsync(flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+  LevelTable tab{nullptr, dminpos, nullptr, 0u};
+  if (ctx.S == 12) launch_leaf_text<12, true>(ctx, d_body, n_local, tab, tmp, flags.ptr, (uint32_t)gpos0);
+  else launch_leaf_text<0, true>(ctx, d_body, n_local, tab, tmp, flags.ptr, (uint32_t)gpos0);
+  BuildFlags h{};
+  STB_CUDA(ctx, cudaMemcpyAsync(&h, flags.ptr, sizeof(h), cudaMemcpyDeviceToHost, ctx.stream));
+  STB_CUDA(ctx, cudaStreamSynchronize(ctx.stream));
+  STB_CUDA(ctx, cudaGetLastError());
+  if (h.bad_symbol != ~0ull) return ctx.fail(STB_ERR_UNKNOWN_SYMBOL, unknown_symbol_message((int)(h.bad_symbol & 0xff)));
+  *non_acgt = (int)h.non_acgt;
   return STB_OK;
 }
 

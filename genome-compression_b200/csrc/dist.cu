@@ -319,6 +319,38 @@ finish_rest_kernel(uint64_t n_pos, uint64_t gpos0, const uint32_t* __restrict__ 
   pointers[pos] = finish_pointer(rank_of(bitmap, word_prefix, n_bits, n_words, q), m & ~IDX_MASK);
 }
 
+// ---- ACGT-only leaves: replicated direct-addressed table instead of the record exchange ----
+constexpr uint32_t DIRECT_EMPTY = 0x7f7f7f7fu;  // > any position, positive as int32 (all-reduce MIN)
+
+__global__ void __launch_bounds__(256)
+direct_mark_kernel(const uint32_t* __restrict__ table, uint32_t entries, uint32_t* __restrict__ bitmap) {
+  const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= entries) return;
+  const uint32_t mp = __ldg(table + s);
+  if (mp < DIRECT_EMPTY) atomicOr(bitmap + (mp >> 5), 1u << (mp & 31));
+}
+
+__global__ void __launch_bounds__(256)
+direct_ids_kernel(const uint32_t* __restrict__ table, uint32_t entries, const uint32_t* __restrict__ bitmap,
+                  const uint32_t* __restrict__ word_prefix, uint64_t n_bits, uint64_t n_words, int S, uint32_t* __restrict__ ids,
+                  unsigned long long* __restrict__ leaves_out) {
+  const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= entries) return;
+  const uint32_t mp = __ldg(table + s);
+  if (mp >= DIRECT_EMPTY) return;
+  const uint32_t id = rank_of(bitmap, word_prefix, n_bits, n_words, mp);
+  ids[s] = id;
+  leaves_out[id] = leaf_from_2bit(s, S);
+}
+
+__global__ void __launch_bounds__(256)
+direct_resolve_kernel(const uint32_t* __restrict__ tmp, uint64_t n, const uint32_t* __restrict__ ids, uint32_t* __restrict__ pointers) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = __ldg(tmp + i);
+  pointers[i] = finish_pointer(__ldg(ids + (t & IDX_MASK)), t & ~IDX_MASK);
+}
+
 }  // namespace stb
 
 using namespace stb;
@@ -440,6 +472,43 @@ int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_i
   if (n_pos) {
     Launch l(t, "dist_finish_rest");
     finish_rest_kernel<<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
+  }
+  STB_CUDA(t, cudaGetLastError());
+  return STB_OK;
+}
+
+int stb_dist_leaf_direct_minpos(stb_tree* ctx, const char* body_dev, uint64_t n_local, uint64_t gpos0, uint32_t* table_dev,
+                                uint32_t* tmp_dev, int* non_acgt) {
+  if (!ctx || !table_dev || !non_acgt || (n_local && (!body_dev || !tmp_dev))) return STB_ERR_INVALID_ARG;
+  if (ctx->S > 12) return ctx->fail(STB_ERR_INVALID_ARG, "direct leaf table needs dna_size <= 12");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
+  if (reinterpret_cast<uintptr_t>(body_dev) & 15u) return ctx->fail(STB_ERR_INVALID_ARG, "body must be 16-byte aligned");
+  if (gpos0 + n_local >= DIRECT_EMPTY) return ctx->fail(STB_ERR_TOO_LARGE, "more than 2^31 leaf positions");
+  return dist_leaf_direct_minpos(*ctx, body_dev, n_local, gpos0, table_dev, tmp_dev, non_acgt);
+}
+
+int stb_dist_leaf_direct_finish(stb_tree* ctx, const uint32_t* table_dev, uint64_t n_level_positions, const uint32_t* tmp_dev,
+                                uint64_t n_local, uint32_t* bitmap_dev, uint32_t* word_prefix_dev, uint32_t* scratch_dev,
+                                uint32_t* ids_dev, uint32_t* pointers_dev, uint64_t* leaves_out_dev) {
+  if (!ctx || !table_dev || !bitmap_dev || !word_prefix_dev || !scratch_dev || !ids_dev || !leaves_out_dev) return STB_ERR_INVALID_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
+  Tree& t = *ctx;
+  cudaStream_t st = t.stream;
+  const uint32_t entries = 1u << (2 * t.S);
+  const uint64_t n_words = ceil_div(n_level_positions, 32);
+  {
+    Launch l(t, "dist_direct_mark");
+    direct_mark_kernel<<<(unsigned)ceil_div(entries, 256), 256, 0, st>>>(table_dev, entries, bitmap_dev);
+  }
+  STB_TRY(stb_dist_rank_index(ctx, bitmap_dev, n_words, word_prefix_dev, scratch_dev));
+  {
+    Launch l(t, "dist_direct_ids");
+    direct_ids_kernel<<<(unsigned)ceil_div(entries, 256), 256, 0, st>>>(table_dev, entries, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
+                                                                        t.S, ids_dev, reinterpret_cast<unsigned long long*>(leaves_out_dev));
+  }
+  if (n_local) {
+    Launch l(t, "dist_direct_resolve");
+    direct_resolve_kernel<<<(unsigned)ceil_div(n_local, 256), 256, 0, st>>>(tmp_dev, n_local, ids_dev, pointers_dev);
   }
   STB_CUDA(t, cudaGetLastError());
   return STB_OK;

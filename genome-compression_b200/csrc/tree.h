@@ -51,6 +51,8 @@ int pack_body(Ctx& ctx, const char* d_body, uint64_t n_leaves, unsigned long lon
 int build_from_body(Tree& t, const char* d_body, uint64_t body_len);
 int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n);
 int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_least_one);
+int dist_leaf_direct_minpos(Ctx& ctx, const char* d_body, uint64_t n_local, uint64_t gpos0, uint32_t* dminpos, uint32_t* tmp,
+                            int* non_acgt);
 
 // dist.cu --------------------------------------------------------------------------
 // (entry points are extern "C", see include/shared_tree_b200_dist.h)

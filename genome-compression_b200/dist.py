@@ -20,6 +20,8 @@ plug in a numpy twin (tests/dist_numpy_stages.py) to exercise this host logic un
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 from dataclasses import dataclass, field
 
 import torch
@@ -37,7 +39,7 @@ class ShardPlan:
     """Which positions of which level a rank owns."""
     n_leaves: int
     world: int
-    cut: int = 1 << 16  # a level with at most this many positions is finished on rank 0
+    cut: int = 1 << 22  # a level with at most this many positions is finished on rank 0 (cheaper than its collectives)
     shard: int = field(init=False)
 
     def __post_init__(self):
@@ -118,6 +120,16 @@ class CudaStages:
                                                  self._p(word_prefix), n_level, self._p(meta), self._p(answers), self._p(pointers),
                                                  self._p(slice_out), self._p(base_count)))
 
+    def leaf_direct_minpos(self, body, n_local, gpos0, table, tmp) -> int:
+        flag = C.c_int(0)
+        self._check(self.pkg.lib.stb_dist_leaf_direct_minpos(self.ctx._h, self._p(body), n_local, gpos0, self._p(table), self._p(tmp), C.byref(flag)))
+        return int(flag.value)
+
+    def leaf_direct_finish(self, table, n_level, tmp, n_local, bitmap, word_prefix, scratch, ids, pointers, leaves_out):
+        self._check(self.pkg.lib.stb_dist_leaf_direct_finish(self.ctx._h, self._p(table), n_level, self._p(tmp), n_local, self._p(bitmap),
+                                                             self._p(word_prefix), self._p(scratch), C.c_void_p(ids.data_ptr()),
+                                                             self._p(pointers), C.c_void_p(leaves_out.data_ptr())))
+
     def upper_levels(self, pointers, n, leaf_pointers):
         tree = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
         tree._check(self.pkg.lib.stb_dist_upper_levels(tree._h, self._p(pointers), n, int(leaf_pointers)))
@@ -174,6 +186,10 @@ class TorchComm:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def all_reduce_min(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+
     def all_gather_object(self, x):
         if self.world == 1:
             return [x]
@@ -225,18 +241,27 @@ class ThreadComm:
         t.copy_(total)
         self.sh.barrier.wait()
 
+    def all_reduce_min(self, t):
+        items = self._exchange(t)
+        total = torch.stack(items).min(dim=0).values
+        self.sh.barrier.wait()
+        t.copy_(total)
+        self.sh.barrier.wait()
+
     def all_gather_object(self, x):
         return self._exchange(x)
 
 
 class DistBuilder:
-    def __init__(self, stages, comm=None, cut: int = 1 << 16):
+    def __init__(self, stages, comm=None, cut: int = 1 << 22):
         self.st = stages
         self.comm = comm or TorchComm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.device = stages.device
         self.cut = cut
         self.collectives = 0
+        self.trace = bool(int(os.environ.get("STB_DIST_TRACE", "0")))
+        self._t0 = time.perf_counter()
 
     # -- collectives ------------------------------------------------------------------
     def _all_to_all(self, send, send_counts, recv_counts):
@@ -257,20 +282,34 @@ class DistBuilder:
         recv = list(counts) if self.rank == dst else [0] * self.world
         return self._all_to_all(t, send, recv)
 
+    def _trace(self, what):
+        """STB_DIST_TRACE=1: synchronising wall-clock trace of every phase (rank 0, debugging only)."""
+        if not self.trace:
+            return
+        self.st.sync()
+        now = time.perf_counter()
+        if self.rank == 0:
+            print(f"[dist] {what:28s} {(now - self._t0) * 1e3:8.3f} ms", flush=True)
+        self._t0 = time.perf_counter()
+
     # -- one level --------------------------------------------------------------------
     def _level(self, kind, items, n_items, gpos0, n_level):
         st, world, dev = self.st, self.world, self.device
+        self._trace(f"-- level n={n_level}")
         n_pos = n_items if kind == LEAF else ceil_div(n_items, 2)
         keys = torch.empty(n_pos, dtype=torch.int64, device=dev)
         gpos = torch.empty(n_pos, dtype=torch.int32, device=dev)
         meta = torch.empty(n_pos, dtype=torch.int32, device=dev)
         counts = torch.zeros(world, dtype=torch.int32, device=dev)
         st.partition(kind, items, n_items, gpos0, world, keys, gpos, meta, counts)
+        self._trace("partition")
         matrix = self._count_matrix(counts)
         send_counts = matrix[self.rank]
         recv_counts = [matrix[src][self.rank] for src in range(world)]
+        self._trace("count matrix")
         rkeys = self._all_to_all(keys, send_counts, recv_counts)
         rgpos = self._all_to_all(gpos, send_counts, recv_counts)
+        self._trace("all_to_all records")
         m = rkeys.shape[0]
         n_words = ceil_div(n_level, 32)
         bitmap = torch.zeros(n_words, dtype=torch.int32, device=dev)
@@ -278,9 +317,12 @@ class DistBuilder:
         cap = max(1024, 2 * m)
         table = st.table(cap)
         st.owner(rkeys, rgpos, m, table, cap, answers, bitmap)
+        self._trace("owner")
         del table, rkeys, rgpos
         back = self._all_to_all(answers, recv_counts, send_counts)
+        self._trace("all_to_all answers")
         self._all_reduce_sum(bitmap)  # first-occurrence bits are disjoint across owners: sum == or
+        self._trace("all_reduce bitmap")
         word_prefix = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
         scratch = torch.empty(ceil_div(n_words, 1024) + 1, dtype=torch.int32, device=dev)
         st.rank_index(bitmap, n_words, word_prefix, scratch)
@@ -288,19 +330,52 @@ class DistBuilder:
         slice_out = torch.empty(n_pos if kind == LEAF else (n_pos, 2), dtype=torch.int64 if kind == LEAF else torch.int32, device=dev)
         base_count = torch.zeros(2, dtype=torch.int32, device=dev)
         st.finish(kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, back, pointers, slice_out, base_count)
+        self._trace("rank index + finish")
         total = word_prefix[n_words:n_words + 1]
         base, count, total = [int(v) & 0xFFFFFFFF for v in torch.cat([base_count, total]).tolist()]
         return pointers, LayerSlice(base, count, slice_out[:count]), total
 
+    def _leaf_level_direct(self, body, n_local, gpos0, n_level):
+        """ACGT-only leaves, dna_size <= 12: replicated direct table + all-reduce(MIN) instead of
+        the record exchange.  Returns None when some rank saw another symbol."""
+        st, dev = self.st, self.device
+        entries = 1 << (2 * st.dna_size)
+        self._trace(f"-- leaf level (direct) n={n_level}")
+        table = torch.full((entries,), 0x7F7F7F7F, dtype=torch.int32, device=dev)
+        tmp = torch.empty(n_local, dtype=torch.int32, device=dev)
+        flag = torch.tensor([st.leaf_direct_minpos(body, n_local, gpos0, table, tmp)], dtype=torch.int32, device=dev)
+        self._all_reduce_sum(flag)
+        if int(flag.item()):
+            return None
+        self._trace("leaf minpos")
+        self.collectives += 1
+        self.comm.all_reduce_min(table)
+        self._trace("all_reduce table")
+        n_words = ceil_div(n_level, 32)
+        bitmap = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        word_prefix = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(ceil_div(n_words, 1024) + 1, dtype=torch.int32, device=dev)
+        ids = torch.empty(entries, dtype=torch.int32, device=dev)
+        pointers = torch.empty(n_local, dtype=torch.int32, device=dev)
+        leaves_out = torch.empty(max(1, min(n_level, entries)), dtype=torch.int64, device=dev)
+        st.leaf_direct_finish(table, n_level, tmp, n_local, bitmap, word_prefix, scratch, ids, pointers, leaves_out)
+        total = int(word_prefix[n_words].item()) & 0xFFFFFFFF
+        self._trace("leaf ids + resolve")
+        # every rank holds the whole (small) leaf table; rank 0's copy is the one that is gathered
+        sl = LayerSlice(0, total, leaves_out[:total]) if self.rank == 0 else LayerSlice(total, 0, leaves_out[:0])
+        return pointers, sl, total
+
     # -- whole build ------------------------------------------------------------------
-    def build_from_leaves(self, local_leaves, n_leaves_total: int) -> DistTree:
+    def build_from_leaves(self, local_leaves, n_leaves_total: int, leaf_level=None) -> DistTree:
         """local_leaves: int64 device tensor with this rank's range of packed leaves
-        (ShardPlan.level_range(rank, 0))."""
+        (ShardPlan.level_range(rank, 0)).  leaf_level: an already finished leaf level."""
         plan = ShardPlan(n_leaves_total, self.world, self.cut)
         lo, hi = plan.level_range(self.rank, 0)
-        assert local_leaves.numel() == hi - lo, (local_leaves.numel(), lo, hi)
         totals, layers = [], []
-        pointers, leaves, total = self._level(LEAF, local_leaves, hi - lo, lo, plan.level_total(0))
+        if leaf_level is None:
+            assert local_leaves.numel() == hi - lo, (local_leaves.numel(), lo, hi)
+            leaf_level = self._level(LEAF, local_leaves, hi - lo, lo, plan.level_total(0))
+        pointers, leaves, total = leaf_level
         totals.append(total)
         n_sharded = plan.sharded_levels()
         for level in range(1, n_sharded):
@@ -326,6 +401,10 @@ class DistBuilder:
         n_leaves_total = n_bases_total // S
         plan = ShardPlan(n_leaves_total, self.world, self.cut)
         lo, hi = plan.level_range(self.rank, 0)
+        if S <= 12:
+            done = self._leaf_level_direct(local_body, hi - lo, lo, plan.level_total(0))
+            if done is not None:
+                return self.build_from_leaves(None, n_leaves_total, leaf_level=done)
         leaves = torch.empty(hi - lo, dtype=torch.int64, device=self.device)
         self.st.pack_body(local_body, hi - lo, leaves)
         return self.build_from_leaves(leaves, n_leaves_total)

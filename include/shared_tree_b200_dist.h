@@ -66,6 +66,22 @@ int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_i
                     const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
                     uint32_t* base_count_dev);
 
+/* Leaf level for ACGT-only input with dna_size <= 12: every rank lowers a replicated
+ * direct-addressed table (4^dna_size uint32, caller-filled with 0x7f7f7f7f) with its GLOBAL
+ * leaf positions straight from the text; the caller all-reduces the table with MIN (as int32);
+ * then every rank derives all leaf ids locally.  *non_acgt = 1: the shard holds other symbols,
+ * use the generic stages (stb_dist_pack_body + partition ...) for the leaf level instead.
+ * tmp_dev[n_local] carries slot | flags between the two calls. */
+int stb_dist_leaf_direct_minpos(stb_tree* ctx, const char* body_dev, uint64_t n_local, uint64_t gpos0, uint32_t* table_dev,
+                                uint32_t* tmp_dev, int* non_acgt);
+/* bitmap_dev: caller-zeroed, ceil(n_level_positions/32) words; word_prefix_dev: that + 1;
+ * scratch_dev as in stb_dist_rank_index; ids_dev: 4^dna_size words; leaves_out_dev receives the
+ * WHOLE leaf table in id order (capacity min(n_level_positions, 4^dna_size)); total =
+ * word_prefix_dev[n_words]. */
+int stb_dist_leaf_direct_finish(stb_tree* ctx, const uint32_t* table_dev, uint64_t n_level_positions, const uint32_t* tmp_dev,
+                                uint64_t n_local, uint32_t* bitmap_dev, uint32_t* word_prefix_dev, uint32_t* scratch_dev,
+                                uint32_t* ids_dev, uint32_t* pointers_dev, uint64_t* leaves_out_dev);
+
 /* Remaining (small) levels on one rank: builds node layers from a pointer array until one
  * pointer is left.  The handle afterwards holds ONLY those layers (stb_layer_count,
  * stb_copy_layer, stb_root work; leaf_count is 0).  leaf_pointers != 0: the array is the leaf

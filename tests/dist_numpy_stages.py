@@ -71,6 +71,50 @@ class NumpyStages:
             assert bad < 0
             leaves_out.numpy().view(np.uint64)[i] = v
 
+    @staticmethod
+    def _two_bit(v, S):
+        code = 0
+        for i in range(S):
+            nib = (v >> (4 * i)) & 0xF
+            if nib not in (1, 2, 4, 8):
+                return None
+            code |= {1: 0, 2: 1, 4: 2, 8: 3}[nib] << (2 * i)
+        return code
+
+    def leaf_direct_minpos(self, body, n_local, gpos0, table, tmp):
+        text, S = body.numpy().tobytes(), self.dna_size
+        tab, t = _u32(table), _u32(tmp)
+        for i in range(n_local):
+            v, bad = self.o.pack(text[i * S:(i + 1) * S], S)
+            assert bad < 0
+            if self._two_bit(v, S) is None:
+                return 1
+            canon, f = self.o.leaf_canonical(v, S)
+            slot = self._two_bit(canon, S)
+            tab[slot] = min(int(tab[slot]), gpos0 + i)
+            t[i] = slot | _flags(f)
+        return 0
+
+    def leaf_direct_finish(self, table, n_level, tmp, n_local, bitmap, word_prefix, scratch, ids, pointers, leaves_out):
+        tab, b = _u32(table), _u32(bitmap)
+        used = np.nonzero(tab < 0x7F7F7F7F)[0]
+        for s_ in used:
+            q = int(tab[s_])
+            b[q >> 5] |= np.uint32(1 << (q & 31))
+        n_words = (n_level + 31) // 32
+        self.rank_index(bitmap, n_words, word_prefix, scratch)
+        wp = _u32(word_prefix)
+        idv, out = _u32(ids), leaves_out.numpy().view(np.uint64)
+        S = self.dna_size
+        for s_ in used:
+            q = int(tab[s_])
+            ident = int(wp[q >> 5]) + bin(int(b[q >> 5]) & ((1 << (q & 31)) - 1)).count("1")
+            idv[s_] = ident
+            out[ident] = sum((1 << ((int(s_) >> (2 * i)) & 3)) << (4 * i) for i in range(S))
+        t, ptr = _u32(tmp), _u32(pointers)
+        for i in range(n_local):
+            ptr[i] = _finish(int(idv[int(t[i]) & IDX]), int(t[i]) & ~IDX & 0xFFFFFFFF)
+
     def partition(self, kind, items, n_items, gpos0, world, keys, gpos, meta, counts):
         recs = self._produce(kind, items, n_items)
         order = sorted(range(len(recs)), key=lambda i: self._owner(recs[i][0], world))  # stable

@@ -42,7 +42,11 @@ def _worker(rank, world, port, n, S, cut, seed, result_path):
         lo, hi = plan.level_range(rank, 0)
         local = torch.from_numpy(leaves[lo:hi].view(np.int64).copy())
         builder = DistBuilder(NumpyStages(oracle, S), cut=cut)
-        tree = builder.build_from_leaves(local, n)
+        if S <= 5 or n < 100:  # text entry point: direct-addressed leaf table + all-reduce(MIN)
+            text = b"".join(pkg.leaf_to_str(v, S).encode() for v in leaves[lo:hi])
+            tree = builder.build_from_body(torch.frombuffer(bytearray(text or b"A"), dtype=torch.uint8), n * S)
+        else:
+            tree = builder.build_from_leaves(local, n)
         full = builder.gather(tree)
         if rank == 0:
             want = oracle.build(leaves, S)

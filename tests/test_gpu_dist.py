@@ -91,3 +91,35 @@ def test_nccl_two_ranks(stb):
            "--master-port", "29531", str(ROOT / "tests" / "dist_gpu_check.py"), "60000000"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "dist_gpu_check ok" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_virtual_ranks_from_text_direct_leaf_table(stb, oracle):
+    """Text entry point: replicated direct-addressed leaf table + all-reduce(MIN); an IUPAC
+    symbol anywhere makes every rank fall back to the record exchange."""
+    import torch
+    from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan, ThreadComm
+
+    for text, S, world in ((corpus_text("merged").upper(), 12, 4), (corpus_text("humhbb").upper(), 5, 3),
+                           (corpus_text("humhbb").upper().replace(b"ACGT", b"ACNT", 3), 12, 2)):
+        n = len(text) // S
+        shared = ThreadComm.Shared(world)
+        plan = ShardPlan(n, world, cut=64)
+        out, errors = [None] * world, []
+
+        def work(rank):
+            try:
+                torch.cuda.set_device(0)
+                lo, hi = plan.level_range(rank, 0)
+                body = torch.frombuffer(bytearray(text[lo * S:hi * S] + b"A" * 16), dtype=torch.uint8).cuda()
+                builder = DistBuilder(CudaStages(stb, S, 0), comm=ThreadComm(shared, rank), cut=64)
+                out[rank] = builder.gather(builder.build_from_body(body, n * S))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+                shared.barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errors, errors
+        want = oracle.build(oracle.fasta_to_leaves(text, S), S)
+        assert out[0].serialize() == want.serialize(), (S, world)
