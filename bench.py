@@ -182,9 +182,8 @@ def algorithmic_bytes(n0: int, leaf_unique: int, layer_unique: list[int]):
     uniq = [leaf_unique] + list(layer_unique)
     pos = [n0] + node_pos
     out = {
-        "leaf_insert": n0 * DNA + 4 * n0,
-        "node_insert": sum(4 * a + 4 * b for a, b in zip(levels[:-1], levels[1:])),
-        "count_first": sum(4 * p + p // 8 for p in pos),
+        "leaf_insert": n0 * DNA + 4 * n0 + n0 // 8,
+        "node_insert": sum(4 * a + 4 * b + b // 8 for a, b in zip(levels[:-1], levels[1:])),
         "assign_ids": sum(p // 8 + 16 * u for p, u in zip(pos, uniq)),
         "resolve_ids": sum(p // 8 + 8 * (p - u) for p, u in zip(pos, uniq)),
     }
@@ -317,9 +316,23 @@ def run_b200_dist(args, world, rank, local_rank):
     import torch.distributed as dist
     from __graft_entry__ import load_package
 
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # NCCL prints its version banner on stdout when the box exports NCCL_DEBUG=VERSION; this
+    # program owes its caller exactly one JSON line there, so stdout points at stderr until the
+    # communicator exists.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)
+        dist.all_to_all_single(torch.empty(world, device="cuda"), torch.zeros(world, device="cuda"))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     pkg = load_package()
     from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan
 

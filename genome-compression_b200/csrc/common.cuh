@@ -150,13 +150,14 @@ __host__ __device__ __forceinline__ unsigned long long leaf_from_2bit(uint32_t c
 }
 
 // ---- hashing -----------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdull;
   k ^= k >> 33;
   k *= 0xc4ceb9fe1a85ec53ull;
-  return (uint32_t)(k >> 32);
+  return k;
 }
+__host__ __device__ __forceinline__ uint32_t hash64(unsigned long long k) { return (uint32_t)(mix64(k) >> 32); }
 
 // 16-byte open-addressing slot, claimed whole by one 128-bit CAS.  `minpos` is the
 // smallest level position that produced the key (atomicMin afterwards).  The last word
@@ -204,14 +205,24 @@ __device__ __forceinline__ void claim_slot(Slot* s, unsigned long long key, uint
 // new: one atomic per position instead of load + CAS + min).
 // Slot `cap` (one past the probed range) is reserved for the key that equals the
 // empty marker (only the 16-nucleotide leaf "----------------" can).
+// First-occurrence bookkeeping without a second pass: whoever becomes a key's minimum toggles
+// its own bit, and toggles the bit of the position it displaced.  XOR commutes, so whatever
+// order those two atomics land in, a bit ends up set iff its position became the minimum and
+// was never displaced - i.e. iff it is the key's first occurrence.
+__device__ __forceinline__ void toggle_bit(uint32_t* bits, uint32_t pos) { atomicXor(bits + (pos >> 5), 1u << (pos & 31)); }
+
+// Probing starts at slot `s`; after `limit` occupied slots it restarts once at `s_alt` (callers
+// that place keys by locality use this to escape a crowded neighbourhood).  `first_bits`
+// (optional) is the level's first-occurrence bitmap, maintained as described above.
 template <bool PROBE_FIRST>
-__device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos) {
-  uint32_t s;
+__device__ __forceinline__ uint32_t table_insert_from(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos, uint32_t s,
+                                                      uint32_t* first_bits = nullptr, uint32_t s_alt = 0,
+                                                      uint32_t limit = 0xffffffffu) {
+  uint32_t steps = 0;
   if (key == EMPTY_KEY) {
     s = cap;
     if (__ldcg(&tab[s].minpos) <= pos) return s;
   } else {
-    s = __umulhi(hash64(key), cap);
     for (;;) {
       unsigned long long k;
       uint32_t mp;
@@ -222,17 +233,31 @@ __device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsign
       }
       if (!probed) {
         claim_slot(tab + s, key, pos, k, mp);
-        if (k == EMPTY_KEY) return s;  // claimed: key and min-position written together
+        if (k == EMPTY_KEY) {  // claimed: key and min-position written together
+          if (first_bits) toggle_bit(first_bits, pos);
+          return s;
+        }
       }
       if (k == key) {
         if (mp <= pos) return s;  // min-position only ever decreases
         break;
       }
-      if (++s == cap) s = 0;
+      if (++steps == limit) s = s_alt;
+      else if (++s == cap) s = 0;
     }
   }
-  atomicMin(&tab[s].minpos, pos);
+  const uint32_t old = atomicMin(&tab[s].minpos, pos);
+  if (first_bits && old > pos) {
+    toggle_bit(first_bits, pos);
+    if (old != 0xffffffffu) toggle_bit(first_bits, old);
+  }
   return s;
+}
+
+template <bool PROBE_FIRST>
+__device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos,
+                                                 uint32_t* first_bits = nullptr) {
+  return table_insert_from<PROBE_FIRST>(tab, cap, key, pos, __umulhi(hash64(key), cap), first_bits);
 }
 #endif
 
