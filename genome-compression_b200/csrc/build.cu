@@ -25,12 +25,8 @@
 #include <cstdlib>
 #include <vector>
 
-#include <cooperative_groups.h>
-
 #include "pack.cuh"
 #include "tree.h"
-
-namespace cg = cooperative_groups;
 
 namespace stb {
 
@@ -119,271 +115,6 @@ leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n
   insert_leaf<DIRECT>(v, S, p, tab, tmp + p, flags);
 }
 
-// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672), for the
-// positions [p_begin, p_end) of the level.
-template <bool PROBE_FIRST>
-__global__ void __launch_bounds__(LVL_THREADS)
-node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p_begin, uint32_t p_end, LevelTable tab,
-                   uint32_t* __restrict__ tmp, const uint32_t* __restrict__ child_unique) {
-  const uint32_t p = p_begin + blockIdx.x * LVL_THREADS + threadIdx.x;
-  if (p >= p_end) return;
-  uint32_t l, r;
-  if (2 * (uint64_t)p + 1 < n_cur) {
-    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
-    l = pr.x;
-    r = pr.y;
-  } else {  // odd tail: node{last, nullptr} (utility.h:17-29)
-    l = cur[2 * (uint64_t)p];
-    r = PTR_NULL;
-  }
-  uint32_t cl, cr, f;
-  canonical_node(l, r, cl, cr, f);
-  const unsigned long long key = ((unsigned long long)cl << 32) | cr;
-  const uint32_t hashed = __umulhi(hash64(key), tab.cap);
-  uint32_t s;
-  if (child_unique) {
-    // Locality placement (node layers above the first): child ids are first-occurrence ranks, so
-    // they grow with the position; a slot proportional to a child id makes neighbouring positions
-    // probe neighbouring slots (one 128-byte line serves several positions instead of one line
-    // per position).  Crowded neighbourhoods (one child with many partners) fall back to the hash.
-    const uint32_t child = ptr_is_null(cl) ? (cr & IDX_MASK) : (cl & IDX_MASK);
-    const uint32_t unique = max(1u, __ldg(child_unique));
-    uint32_t near = (uint32_t)(((unsigned long long)child * tab.cap) / unique) + (hashed & 7u);
-    if (near >= tab.cap) near = tab.cap - 1;
-    s = table_insert_from<PROBE_FIRST>(tab.slots, tab.cap, key, p, near, tab.first_bits, hashed, 24u);
-  } else {
-    s = table_insert_from<PROBE_FIRST>(tab.slots, tab.cap, key, p, hashed, tab.first_bits);
-  }
-  tmp[p] = s | f;
-}
-
-// ---- hash-partitioned node level ----------------------------------------------------------
-// A random slot access costs a whole 128-byte line of HBM traffic (profiles/README.md), so a
-// large level is first split by key hash into buckets small enough that a bucket's table stays
-// in L2; the (key, position) records then stream through HBM once, 12 bytes each, and the
-// table itself never leaves the cache.  Buckets are processed in batches of PART_BATCH tables.
-constexpr int PART_THREADS = 256;
-constexpr int PART_WARPS = PART_THREADS / 32;
-constexpr int PART_GROUPS = 16;                          // 32-record groups per warp
-constexpr int PART_TILE = PART_THREADS * PART_GROUPS;    // 4096 positions per CTA
-constexpr int PART_WARP_ITEMS = 32 * PART_GROUPS;
-constexpr int PART_MAX_BUCKETS = 512;
-
-__device__ __forceinline__ void node_key_at(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p, unsigned long long& key,
-                                            uint32_t& flags) {
-  uint32_t l, r;
-  if (2 * (uint64_t)p + 1 < n_cur) {
-    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
-    l = pr.x;
-    r = pr.y;
-  } else {
-    l = cur[2 * (uint64_t)p];
-    r = PTR_NULL;
-  }
-  uint32_t cl, cr;
-  canonical_node(l, r, cl, cr, flags);
-  key = ((unsigned long long)cl << 32) | cr;
-}
-
-// bucket = top bits of one hash, slot inside the bucket's table = another hash
-__device__ __forceinline__ uint32_t bucket_of(unsigned long long key, int log2_buckets) {
-  return log2_buckets ? hash64(key) >> (32 - log2_buckets) : 0u;
-}
-
-__global__ void __launch_bounds__(PART_THREADS)
-part_hist_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_pos, int log2_buckets, uint32_t nblocks,
-                 uint32_t* __restrict__ hist) {
-  extern __shared__ uint32_t bins[];
-  const uint32_t buckets = 1u << log2_buckets;
-  for (uint32_t b = threadIdx.x; b < buckets; b += PART_THREADS) bins[b] = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t warp_first = blockIdx.x * PART_TILE + warp * PART_WARP_ITEMS;
-#pragma unroll 4
-  for (int g = 0; g < PART_GROUPS; ++g) {
-    const uint32_t p = warp_first + g * 32 + lane;
-    uint32_t b = 0xffffffffu;
-    if (p < n_pos) {
-      unsigned long long key;
-      uint32_t f;
-      node_key_at(cur, n_cur, p, key, f);
-      b = bucket_of(key, log2_buckets);
-    }
-    const uint32_t peers = __match_any_sync(0xffffffffu, b);
-    if (p < n_pos && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&bins[b], (uint32_t)__popc(peers));
-  }
-  __syncthreads();
-  for (uint32_t b = threadIdx.x; b < buckets; b += PART_THREADS) hist[b * nblocks + blockIdx.x] = bins[b];
-}
-
-// one CTA per bucket: exclusive scan of its row of per-CTA counts + bucket total
-__global__ void __launch_bounds__(1024) part_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ row_total) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nblocks; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nblocks ? row[i] : 0u;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t before = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - v;
-    if (i < nblocks) row[i] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = before + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) row_total[blockIdx.x] = carry_s;
-}
-
-// bucket_off[b] = records before bucket b (single CTA, <= 1024 buckets); bucket_off[buckets] = total
-__global__ void __launch_bounds__(1024) part_offsets_kernel(const uint32_t* __restrict__ row_total, uint32_t buckets,
-                                                            uint32_t* __restrict__ bucket_off) {
-  __shared__ uint32_t warp_sum[32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t v = threadIdx.x < buckets ? row_total[threadIdx.x] : 0u;
-  uint32_t x = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-    if (lane >= d) x += y;
-  }
-  if (lane == 31) warp_sum[warp] = x;
-  __syncthreads();
-  uint32_t before = 0;
-  for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
-  if (threadIdx.x < buckets) bucket_off[threadIdx.x] = before + x - v;
-  if (threadIdx.x == buckets - 1) bucket_off[buckets] = before + x;
-}
-
-// Scatter pass.  The tile's records are first ordered by bucket in shared memory, then written
-// out: consecutive threads write consecutive records of one bucket, so the stores leave the SM as
-// runs instead of one 32-byte sector per lane (the un-staged version was L2-request bound: 8.3 ms
-// instead of ~1.5 ms per 3.1 Gbp).
-struct PartSmem {
-  unsigned long long key[PART_TILE];
-  uint32_t meta[PART_TILE];
-  uint32_t tile_off[PART_MAX_BUCKETS + 1];   // tile-local exclusive prefix of bucket counts
-  uint32_t gbase[PART_MAX_BUCKETS];          // global index of this tile's first record of bucket b
-  uint32_t warp_cnt[PART_WARPS * PART_MAX_BUCKETS];
-};
-
-__global__ void __launch_bounds__(PART_THREADS)
-part_scatter_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_pos, int log2_buckets, uint32_t nblocks,
-                    const uint32_t* __restrict__ hist, const uint32_t* __restrict__ bucket_off,
-                    unsigned long long* __restrict__ rec_key, uint32_t* __restrict__ rec_meta) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  PartSmem& sm = *reinterpret_cast<PartSmem*>(smem_raw);
-  const uint32_t buckets = 1u << log2_buckets;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t i = threadIdx.x; i < PART_WARPS * buckets; i += PART_THREADS) sm.warp_cnt[i] = 0;
-  __syncthreads();
-  const uint32_t tile_first = blockIdx.x * PART_TILE;
-  const uint32_t warp_first = tile_first + warp * PART_WARP_ITEMS;
-  unsigned long long key[PART_GROUPS];
-  uint32_t meta[PART_GROUPS], bkt[PART_GROUPS];
-  uint32_t* mine = sm.warp_cnt + warp * buckets;
-#pragma unroll
-  for (int g = 0; g < PART_GROUPS; ++g) {
-    const uint32_t p = warp_first + g * 32 + lane;
-    bkt[g] = 0xffffffffu;
-    key[g] = 0;
-    meta[g] = 0;
-    if (p < n_pos) {
-      uint32_t f;
-      node_key_at(cur, n_cur, p, key[g], f);
-      meta[g] = p | f;
-      bkt[g] = bucket_of(key[g], log2_buckets);
-    }
-    const uint32_t peers = __match_any_sync(0xffffffffu, bkt[g]);
-    if (p < n_pos && lane == (uint32_t)(__ffs(peers) - 1)) mine[bkt[g]] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  // per bucket: tile count, exclusive scan over the warps (tile-local offsets), global base
-  for (uint32_t b = threadIdx.x; b < buckets; b += PART_THREADS) {
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < PART_WARPS; ++w) {
-      const uint32_t c = sm.warp_cnt[w * buckets + b];
-      sm.warp_cnt[w * buckets + b] = run;
-      run += c;
-    }
-    sm.tile_off[b] = run;  // count for now
-    sm.gbase[b] = bucket_off[b] + hist[b * nblocks + blockIdx.x];
-  }
-  __syncthreads();
-  if (warp == 0) {  // exclusive scan of the bucket counts (<= 1024 entries, 32 per lane)
-    const uint32_t per = (buckets + 31) / 32;
-    uint32_t sum = 0;
-    for (uint32_t j = 0; j < per; ++j) {
-      const uint32_t b = lane * per + j;
-      if (b < buckets) sum += sm.tile_off[b];
-    }
-    uint32_t x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    uint32_t run = x - sum;
-    for (uint32_t j = 0; j < per; ++j) {
-      const uint32_t b = lane * per + j;
-      if (b < buckets) {
-        const uint32_t c = sm.tile_off[b];
-        sm.tile_off[b] = run;
-        run += c;
-      }
-    }
-    if (lane == 31) sm.tile_off[buckets] = run;
-  }
-  __syncthreads();
-  // stage: record -> tile-local slot (bucket order, stable inside a bucket)
-#pragma unroll
-  for (int g = 0; g < PART_GROUPS; ++g) {
-    const uint32_t p = warp_first + g * 32 + lane;
-    const bool ok = p < n_pos;
-    const uint32_t peers = __match_any_sync(0xffffffffu, bkt[g]);
-    uint32_t li = 0;
-    if (ok) li = sm.tile_off[bkt[g]] + mine[bkt[g]] + __popc(peers & ((1u << lane) - 1u));
-    __syncwarp();
-    if (ok && lane == (uint32_t)(__ffs(peers) - 1)) mine[bkt[g]] += __popc(peers);
-    __syncwarp();
-    if (ok) {
-      sm.key[li] = key[g];
-      sm.meta[li] = meta[g];
-    }
-  }
-  __syncthreads();
-  // write out in staged order: runs of one bucket are contiguous in HBM
-  const uint32_t here = sm.tile_off[buckets];
-  for (uint32_t j = threadIdx.x; j < here; j += PART_THREADS) {
-    const unsigned long long k = sm.key[j];
-    const uint32_t b = bucket_of(k, log2_buckets);
-    const uint32_t dst = sm.gbase[b] + (j - sm.tile_off[b]);
-    rec_key[dst] = k;
-    rec_meta[dst] = sm.meta[j];
-  }
-}
-
 // 128-bit CAS with an arbitrary expected value; returns the previous contents.
 __device__ __forceinline__ void cas_slot(Slot* s, unsigned long long exp_lo, unsigned long long exp_hi, unsigned long long new_lo,
                                          unsigned long long new_hi, unsigned long long& old_lo, unsigned long long& old_hi) {
@@ -400,114 +131,74 @@ __device__ __forceinline__ void cas_slot(Slot* s, unsigned long long exp_lo, uns
       : "memory");
 }
 
-// Insert into a table whose slots carry an epoch tag in their last word: a slot whose tag is not
-// `serial` is stale, i.e. empty, so tables are reused batch after batch without being cleared.
-__device__ __forceinline__ uint32_t tagged_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos, uint32_t serial) {
-  uint32_t s = __umulhi((uint32_t)mix64(key), cap);
+// Node-level insert into an epoch-tagged table: a slot whose last word is not `serial` is stale
+// (left by an earlier level), i.e. empty; it is claimed by a 128-bit CAS against exactly what was
+// read, writing key, min-position and tag at once.  Probing starts at `s`; after `limit` occupied
+// slots it restarts once at `s_alt`.  Keeps the first-occurrence bitmap current (toggle_bit).
+__device__ __forceinline__ uint32_t tagged_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos, uint32_t serial,
+                                                  uint32_t s, uint32_t s_alt, uint32_t limit, uint32_t* first_bits) {
   const unsigned long long fresh_hi = ((unsigned long long)serial << 32) | pos;
+  uint32_t steps = 0;
   for (;;) {
     unsigned long long k, w;
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(w) : "l"(tab + s));
     if ((uint32_t)(w >> 32) != serial) {
       unsigned long long ok, ow;
       cas_slot(tab + s, k, w, key, fresh_hi, ok, ow);
-      if (ok == k && ow == w) return s;  // claimed with key and min-position in one atomic
+      if (ok == k && ow == w) {
+        toggle_bit(first_bits, pos);
+        return s;
+      }
       k = ok;
       w = ow;  // somebody else claimed it in this epoch
     }
     if (k == key) {
-      if ((uint32_t)w > pos) atomicMin(&tab[s].minpos, pos);
+      if ((uint32_t)w > pos) {
+        const uint32_t old = atomicMin(&tab[s].minpos, pos);
+        if (old > pos) {
+          toggle_bit(first_bits, pos);
+          toggle_bit(first_bits, old);
+        }
+      }
       return s;
     }
-    if (++s == cap) s = 0;
+    if (++steps == limit) s = s_alt;
+    else if (++s == cap) s = 0;
   }
 }
 
-constexpr int BK_PER_THREAD = 2;                 // independent probe chains in flight per thread
-constexpr int BK_TILE = 256 * BK_PER_THREAD;     // records per CTA
-
-// Bucket b owns the table region [2*off[b], 2*off[b+1]) (twice its record count), so the whole
-// level's tables are exactly as large as the un-partitioned table and no bucket can overflow,
-// whatever the skew.  Records are stored bucket after bucket and CTAs are dispatched in index
-// order, so at any moment only a few buckets' regions are being touched; each CTA first prefetches
-// its share of its bucket's region into L2 (a streaming read) so the random probes that follow
-// hit L2 instead of each missing to HBM.
-__device__ __forceinline__ void prefetch_table_share(const Slot* tables, const uint32_t* __restrict__ bucket_off, uint32_t buckets,
-                                                     uint32_t b, uint32_t first_record) {
-  // The CTAs of bucket b run together; what they stream in is the region of bucket b + 1, whose
-  // CTAs come next, so that bucket's probes find their lines already in L2.
-  const uint32_t begin = bucket_off[b], count = bucket_off[b + 1] - begin;
-  const uint32_t blocks_in_bucket = (count + BK_TILE - 1) / BK_TILE;
-  const uint32_t rank = (first_record - begin) / BK_TILE;
-  if (b + 1 >= buckets) return;
-  const uint32_t next_begin = bucket_off[b + 1], next_count = bucket_off[b + 2] - next_begin;
-  const uint32_t lines = (next_count * 2 * (uint32_t)sizeof(Slot) + 127) / 128;  // 128-byte lines of the region
-  const uint32_t per_block = (lines + blocks_in_bucket - 1) / blocks_in_bucket;
-  const char* region = reinterpret_cast<const char*>(tables + 2 * (size_t)next_begin);
-  for (uint32_t j = threadIdx.x; j < per_block; j += 256) {
-    const uint32_t line = rank * per_block + j;
-    if (line < lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(region + (size_t)line * 128));
+// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
+__global__ void __launch_bounds__(LVL_THREADS)
+node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
+                   const uint32_t* __restrict__ child_unique, uint32_t serial) {
+  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= n_next) return;
+  uint32_t l, r;
+  if (2 * (uint64_t)p + 1 < n_cur) {
+    const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
+    l = pr.x;
+    r = pr.y;
+  } else {  // odd tail: node{last, nullptr} (utility.h:17-29)
+    l = cur[2 * (uint64_t)p];
+    r = PTR_NULL;
   }
-}
-
-__global__ void __launch_bounds__(256)
-bucket_insert_kernel(const unsigned long long* __restrict__ rec_key, const uint32_t* __restrict__ rec_meta, uint32_t n,
-                     const uint32_t* __restrict__ bucket_off, int log2_buckets, Slot* tables, uint32_t serial,
-                     uint32_t* __restrict__ rec_slot) {
-  const uint32_t i0 = blockIdx.x * BK_TILE;
-  prefetch_table_share(tables, bucket_off, 1u << log2_buckets, bucket_of(rec_key[i0], log2_buckets), i0);
-  unsigned long long key[BK_PER_THREAD];
-  uint32_t pos[BK_PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) {
-    const uint32_t i = i0 + j * 256 + threadIdx.x;
-    key[j] = i < n ? rec_key[i] : 0ull;
-    pos[j] = i < n ? rec_meta[i] & IDX_MASK : 0u;
+  uint32_t cl, cr, f;
+  canonical_node(l, r, cl, cr, f);
+  const unsigned long long key = ((unsigned long long)cl << 32) | cr;
+  const uint32_t hashed = __umulhi(hash64(key), tab.cap);
+  uint32_t start = hashed, limit = 0xffffffffu;
+  if (child_unique) {
+    // Locality placement (node layers above the first): child ids are first-occurrence ranks, so
+    // they grow with the position; a slot proportional to a child id makes neighbouring positions
+    // probe neighbouring slots (one 128-byte line serves several positions instead of one line
+    // per position).  Crowded neighbourhoods (one child with many partners) fall back to the hash.
+    const uint32_t child = ptr_is_null(cl) ? (cr & IDX_MASK) : (cl & IDX_MASK);
+    const uint32_t unique = max(1u, __ldg(child_unique));
+    start = (uint32_t)(((unsigned long long)child * tab.cap) / unique) + (hashed & 7u);
+    if (start >= tab.cap) start = tab.cap - 1;
+    limit = 24u;
   }
-  Slot* tab[BK_PER_THREAD];
-  uint32_t cap[BK_PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) {
-    const uint32_t b = bucket_of(key[j], log2_buckets);
-    const uint32_t begin = __ldg(bucket_off + b);
-    cap[j] = 2 * (__ldg(bucket_off + b + 1) - begin);
-    tab[j] = tables + 2 * (size_t)begin;
-  }
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) {
-    const uint32_t i = i0 + j * 256 + threadIdx.x;
-    if (i < n) rec_slot[i] = tagged_insert(tab[j], cap[j], key[j], pos[j], serial);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-bucket_answer_kernel(const unsigned long long* __restrict__ rec_key, const uint32_t* __restrict__ rec_meta, uint32_t n,
-                     const uint32_t* __restrict__ rec_slot, const uint32_t* __restrict__ bucket_off, int log2_buckets,
-                     const Slot* tables, uint32_t* __restrict__ bitmask, uint32_t* __restrict__ tmp) {
-  const uint32_t i0 = blockIdx.x * BK_TILE;
-  prefetch_table_share(tables, bucket_off, 1u << log2_buckets, bucket_of(rec_key[i0], log2_buckets), i0);
-  uint32_t meta[BK_PER_THREAD], q[BK_PER_THREAD];
-  const uint32_t* where[BK_PER_THREAD];
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) {
-    const uint32_t i = i0 + j * 256 + threadIdx.x;
-    meta[j] = 0;
-    where[j] = nullptr;
-    if (i < n) {
-      meta[j] = rec_meta[i];
-      const uint32_t begin = __ldg(bucket_off + bucket_of(rec_key[i], log2_buckets));
-      where[j] = &tables[2 * (size_t)begin + rec_slot[i]].minpos;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) q[j] = where[j] ? __ldcg(where[j]) : 0u;
-#pragma unroll
-  for (int j = 0; j < BK_PER_THREAD; ++j) {
-    if (!where[j]) continue;
-    const uint32_t pos = meta[j] & IDX_MASK;
-    if (q[j] == pos) atomicOr(bitmask + (pos >> 5), 1u << (pos & 31));
-    else tmp[pos] = (meta[j] & ~IDX_MASK) | q[j];
-  }
+  tmp[p] = tagged_insert(tab.slots, tab.cap, key, p, serial, start, hashed, limit, tab.first_bits) | f;
 }
 
 // per-CTA first-occurrence counts (LVL_TILE positions = 32 bitmask words) for the scan
@@ -630,7 +321,7 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
 // left in tmp[p].
 template <bool DIRECT>
 __global__ void __launch_bounds__(LVL_THREADS)
-resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask, bool via_position) {
+resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask) {
   const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
@@ -641,9 +332,7 @@ resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uin
         const uint32_t t = tmp[p];
         const uint32_t s = t & IDX_MASK;
         // hash levels: slot -> position of the first occurrence -> its finished pointer -> id
-        // (the partitioned path already left the position instead of the slot: via_position)
-        const uint32_t id = DIRECT ? __ldcg(tab.dids + s)
-                                   : (__ldcg(tmp + (via_position ? s : __ldcg(&tab.slots[s].minpos))) & IDX_MASK);
+        const uint32_t id = DIRECT ? __ldcg(tab.dids + s) : (__ldcg(tmp + __ldcg(&tab.slots[s].minpos)) & IDX_MASK);
         tmp[p] = finish_pointer(id, t & ~IDX_MASK);
       }
     }
@@ -681,7 +370,7 @@ void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, ui
 // count -> scan -> assign -> resolve for one level whose inserts are already queued.
 template <int MODE>
 void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& sc, uint32_t* total_out, void* uniq,
-                  const uint32_t* children = nullptr, uint32_t n_children = 0, bool via_position = false) {
+                  const uint32_t* children = nullptr, uint32_t n_children = 0) {
   constexpr bool DIRECT = (MODE == MODE_LEAF_DIRECT);
   const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
   {  // the inserts kept the first-occurrence bitmap current: count it per CTA tile for the scan
@@ -698,7 +387,7 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
   }
   {
     Launch l(ctx, "resolve_ids");
-    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, via_position);
+    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr);
   }
 }
 
@@ -706,65 +395,6 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
 static uint64_t env_u64(const char* name, uint64_t fallback) {
   const char* v = getenv(name);
   return v ? strtoull(v, nullptr, 0) : fallback;
-}
-
-// insert + classify of one large node level through hash buckets with L2-resident tables.
-// Leaves the level's first-occurrence bitmask set and, for later occurrences, the position of
-// the first one in tmp[] (finish_level is told via_position).
-int partitioned_insert_count(Tree& t, Scratch& sc, const uint32_t* cur, uint64_t n_cur, uint32_t* nxt, uint64_t n_next) {
-  cudaStream_t st = t.stream;
-  static const uint64_t bucket_target = env_u64("STB_PART_BUCKET", 1ull << 18);
-  int log2p = 0;
-  while (log2p < 9 && (n_next >> log2p) > bucket_target) ++log2p;
-  const uint32_t buckets = 1u << log2p;
-  const uint32_t nblocks = (uint32_t)ceil_div(n_next, PART_TILE);
-  DevBuf<uint32_t> hist, row_total, bucket_off, rec_meta, rec_slot;
-  DevBuf<unsigned long long> rec_key;
-  STB_CUDA(t, hist.alloc((uint64_t)buckets * nblocks, st));
-  STB_CUDA(t, row_total.alloc(buckets, st));
-  STB_CUDA(t, bucket_off.alloc(buckets + 1, st));
-  STB_CUDA(t, rec_key.alloc(n_next, st));
-  STB_CUDA(t, rec_meta.alloc(n_next, st));
-  STB_CUDA(t, rec_slot.alloc(n_next, st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    STB_CUDA(t, cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem)));
-    attr_set = true;
-  }
-  {
-    Launch l(t, "part_hist");
-    part_hist_kernel<<<nblocks, PART_THREADS, buckets * 4, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, log2p, nblocks, hist.ptr);
-  }
-  {
-    Launch l(t, "part_scan");
-    part_rowscan_kernel<<<buckets, 1024, 0, st>>>(hist.ptr, nblocks, row_total.ptr);
-    part_offsets_kernel<<<1, 1024, 0, st>>>(row_total.ptr, buckets, bucket_off.ptr);
-  }
-  {
-    Launch l(t, "part_scatter");
-    part_scatter_kernel<<<nblocks, PART_THREADS, sizeof(PartSmem), st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, log2p, nblocks, hist.ptr,
-                                                                        bucket_off.ptr, rec_key.ptr, rec_meta.ptr);
-  }
-  const uint64_t mask_words = ceil_div(n_next, LVL_TILE) * (LVL_TILE / 32);
-  STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, mask_words * 4, st));
-  if (!sc.tags_cleared) {  // once per build: every later level uses a fresh epoch tag instead of clearing
-    Launch l(t, "table_clear", false);
-    STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, sc.slots.bytes(), st));
-    sc.tags_cleared = true;
-  }
-  const uint32_t serial = ++sc.serial;
-  const unsigned nb = (unsigned)ceil_div(n_next, BK_TILE);
-  {
-    Launch l(t, "bucket_insert");
-    bucket_insert_kernel<<<nb, 256, 0, st>>>(rec_key.ptr, rec_meta.ptr, (uint32_t)n_next, bucket_off.ptr, log2p, sc.slots.ptr, serial, rec_slot.ptr);
-  }
-  {
-    Launch l(t, "bucket_answer");
-    bucket_answer_kernel<<<nb, 256, 0, st>>>(rec_key.ptr, rec_meta.ptr, (uint32_t)n_next, rec_slot.ptr, bucket_off.ptr, log2p, sc.slots.ptr,
-                                             sc.bitmask.ptr, nxt);
-  }
-  STB_CUDA(t, cudaGetLastError());
-  return STB_OK;
 }
 
 // Node levels from a pointer array down to a single root pointer.  Appends one layer per
@@ -782,27 +412,24 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     STB_CUDA(t, layer.nodes.alloc(n_next, st));
     LevelTable nt{sc.slots.ptr, nullptr, nullptr, table_cap(n_next)};
     nt.first_bits = sc.bitmask.ptr;
-    bool via_position = false;
-    static const uint64_t part_min = env_u64("STB_PART_MIN", ~0ull);  // experimental, off (profiles/README.md)
-    if (n_next >= part_min) {
-      STB_TRY(partitioned_insert_count(t, sc, cur, n_cur, nxt, n_next));
-      via_position = true;
-    } else {
-    {
+    if (!sc.tags_cleared) {
+      // Node tables are never cleared between levels: a slot's last word is an epoch tag and a
+      // slot whose tag is not this level's serial counts as empty.  One clear per build.
       Launch l(t, "table_clear", false);
-      STB_CUDA(t, cudaMemsetAsync(nt.slots, 0xff, ((uint64_t)nt.cap + 1) * sizeof(Slot), st));
-      STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n_next, LVL_TILE) * (LVL_TILE / 8), st));
+      STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, sc.slots.bytes(), st));
+      sc.tags_cleared = true;
     }
+    STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n_next, LVL_TILE) * (LVL_TILE / 8), st));
     {
       // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
-      // and chunking insert+count to keep table lines in L2 did not pay (profiles/README.md).
+      // and chunking the level to keep table lines in L2 did not pay (profiles/README.md).
       Launch l(t, "node_insert");
       // children of level 0 are leaf ids (or an imported array): not position-ordered
       const uint32_t* child_unique = (locality && level > 0) ? counts_dev + level - 1 : nullptr;
-      node_insert_kernel<true><<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, 0u, (uint32_t)n_next, nt, nxt, child_unique);
+      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
+                                                                                          ++sc.serial);
     }
-    }
-    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur, via_position);
+    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
     std::swap(cur, nxt);
     n_cur = n_next;
     ++level;

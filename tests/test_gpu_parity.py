@@ -258,15 +258,3 @@ def test_large_properties(stb):
     # idempotence: sorting a sorted tree changes nothing
     tree.sort()
     assert hashlib.sha256(tree.serialize()).digest() == hashlib.sha256(stream).digest()
-
-
-@pytest.mark.parametrize("bucket", [64, 4096])
-def test_partitioned_node_levels_forced_small(bucket):
-    """The hash-partitioned node-level path, forced on for small inputs (see tests/partitioned_check.py)."""
-    import os
-    import subprocess
-    import sys
-    from conftest import ROOT
-    env = dict(os.environ, STB_PART_MIN="1", STB_PART_BUCKET=str(bucket), STB_PART_L2_MB="1")
-    res = subprocess.run([sys.executable, str(ROOT / "tests" / "partitioned_check.py")], env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0 and "partitioned_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
