@@ -103,6 +103,68 @@ leaf_insert_text_kernel(const char* __restrict__ body, uint64_t n_leaves, int S_
   }
 }
 
+// ACGT fast path for the default leaf length (12): the whole leaf level in 32-bit registers.
+// Four text bytes -> four 2-bit codes by SWAR (A0 C1 G2 T3; any other byte, in either case,
+// fails the check), twelve of them = one 24-bit word whose numeric order equals the order of
+// the reference's 4-bit words (A1<C2<G4<T8, same nucleotide significance), so the canonical
+// variant (dna.cpp:135-143) is the minimum of {c, ~c, reverse(c), reverse(~c)} taken on that
+// word, and the word itself is the direct-table index.  Anything that is not pure ACGT raises
+// the non_acgt flag and the host re-runs the level through the general kernel.
+__device__ __forceinline__ bool acgt_word_to_2bit(uint32_t w, uint32_t& out8) {
+  const uint32_t u = w & 0xDFDFDFDFu;                       // fold case
+  const uint32_t x = (u >> 1) & 0x03030303u;                // A0 C1 G3 T2
+  const uint32_t idx = x ^ ((x >> 1) & 0x01010101u);        // A0 C1 G2 T3
+  const uint32_t b0 = idx & 0x01010101u, b1 = (idx >> 1) & 0x01010101u, bb = b0 & b1;
+  // the byte each code must have come from: 'A' + {0, 2, 6, 0x13}
+  const uint32_t expect = 0x41414141u + (b0 << 1) + (b1 << 1) + (b1 << 2) + bb + (bb << 1) + (bb << 3);
+  out8 = (idx * 0x01041040u) >> 24;                          // 4 codes -> 8 bits, first char lowest
+  return expect == u;
+}
+
+__device__ __forceinline__ uint32_t reverse_2bit_24(uint32_t c) {
+  const uint32_t r = __brev(c) >> 8;  // reverses the pairs and the bits inside each pair
+  return ((r & 0x555555u) << 1) | ((r >> 1) & 0x555555u);
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+leaf_insert_acgt12_kernel(const char* __restrict__ body, uint64_t n_leaves, LevelTable tab, uint32_t* __restrict__ tmp,
+                          BuildFlags* flags, uint32_t pos0) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* tile = smem + 256;  // same layout as the general kernel (the table area is unused here)
+  const uint64_t tile_first = (uint64_t)blockIdx.x * PACK_TILE_LEAVES;
+  const uint32_t here = (uint32_t)min((uint64_t)PACK_TILE_LEAVES, n_leaves - tile_first);
+  stage_text_tile(smem, tile, body + tile_first * 12, here * 12u);
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(tile);
+#pragma unroll
+  for (int it = 0; it < PACK_LEAVES_PER_THREAD; ++it) {
+    const uint32_t j = it * PACK_THREADS + threadIdx.x;
+    if (j >= here) continue;
+    uint32_t c0, c1, c2;
+    const bool ok = acgt_word_to_2bit(words[3 * j], c0) & acgt_word_to_2bit(words[3 * j + 1], c1) & acgt_word_to_2bit(words[3 * j + 2], c2);
+    if (!ok) {
+      flags->non_acgt = 1u;
+      tmp[tile_first + j] = 0u;
+      continue;
+    }
+    const uint32_t c = c0 | (c1 << 8) | (c2 << 16);
+    const uint32_t t = ~c & 0xFFFFFFu, m = reverse_2bit_24(c), i = ~m & 0xFFFFFFu;
+    uint32_t best = c, f = 0;
+    if (t < best) { best = t; f = TRANSPOSE; }
+    if (m < best) { best = m; f = MIRROR; }
+    if (i < best) { best = i; f = MIRROR | TRANSPOSE; }
+    if (c == m) f |= INVARIANT;
+    const uint32_t pos = pos0 + (uint32_t)(tile_first + j);
+    if (__ldcg(tab.dminpos + best) > pos) {
+      const uint32_t old = atomicMin(tab.dminpos + best, pos);
+      if (tab.first_bits && old > pos) {
+        toggle_bit(tab.first_bits, pos);
+        if (old != 0xffffffffu) toggle_bit(tab.first_bits, old);
+      }
+    }
+    tmp[tile_first + j] = best | f;
+  }
+}
+
 // Leaves from a packed array (the std::vector<dna> constructor, shared_tree.cpp:212).
 template <bool DIRECT>
 __global__ void __launch_bounds__(LVL_THREADS)
@@ -213,7 +275,9 @@ bitmask_blockcnt_kernel(const uint32_t* __restrict__ bitmask, uint32_t n_blocks,
   if (lane == 0) blockcnt[blk] = c;
 }
 
-// In-place exclusive scan of the per-CTA counts (single CTA); total -> *total_out.
+// In-place exclusive scan of the per-CTA counts (single CTA, 16 entries per thread and
+// round); total -> *total_out.
+constexpr int SCAN_PER_THREAD = 16;
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ cnt, uint32_t nb,
                                                            uint32_t* __restrict__ total_out) {
   __shared__ uint32_t warp_sum[32];
@@ -221,10 +285,16 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict_
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < nb; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nb ? cnt[i] : 0u;
-    uint32_t x = v;
+  for (uint32_t base = 0; base < nb; base += 1024 * SCAN_PER_THREAD) {
+    const uint32_t i0 = base + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+      v[j] = i0 + j < nb ? cnt[i0 + j] : 0u;
+      sum += v[j];
+    }
+    uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -242,11 +312,14 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict_
       warp_sum[lane] = w;  // inclusive over warps
     }
     __syncthreads();
-    const uint32_t carry = carry_s;
-    const uint32_t before = carry + (warp ? warp_sum[warp - 1] : 0u) + x - v;
-    if (i < nb) cnt[i] = before;
+    uint32_t run = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - sum;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+      if (i0 + j < nb) cnt[i0 + j] = run;
+      run += v[j];
+    }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = before + v;
+    if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
   if (threadIdx.x == 0) *total_out = carry_s;
@@ -363,6 +436,10 @@ template <int S_T, bool DIRECT>
 void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags, uint32_t pos0 = 0) {
   const size_t smem = pack_smem_bytes(ctx.S);
   Launch l(ctx, "leaf_insert");
+  if (S_T == 12 && DIRECT) {
+    leaf_insert_acgt12_kernel<<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(body, n, tab, tmp, flags, pos0);
+    return;
+  }
   leaf_insert_text_kernel<S_T, DIRECT><<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(
       body, n, ctx.S, tab, tmp, flags, pos0);
 }
