@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-bases", type=int, default=0, help="0 = auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip sort/serialize/decode/random-access timings")
     return ap.parse_args()
 
 
@@ -289,6 +290,47 @@ def run_b200(args):
                "d2h_bytes_per_step": 4 * (len(counts) + 1) + 4 + 16, "ms_per_step": dt * 1e3, "steps": reps}
         del host
 
+    # ---- the rest of the path at the same size: sort_tree, bytes/serialize, decode, random access ----
+    pipeline = None
+    if not args.no_pipeline:
+        def timed(fn, reps=1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(stream)
+            for _ in range(reps):
+                out = fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, out
+
+        tree.build_from_body(text)
+        sort_ms, _ = timed(tree.sort)
+        plan_ms, stream_bytes = timed(tree.bytes)
+        dag = torch.empty(stream_bytes + 16, dtype=torch.uint8, device="cuda")
+        ser_ms, _ = timed(lambda: tree.serialize_into(dag))
+        out = torch.empty(n0 * DNA, dtype=torch.uint8, device="cuda")
+        dec_ms, _ = timed(lambda: tree.decode_ascii(out=out))
+        roundtrip_ok = bool(torch.equal(out, text[: n0 * DNA]))
+        del out
+        leaves_out = torch.empty(n0, dtype=torch.int64, device="cuda")
+        decl_ms, _ = timed(lambda: tree.decode(out=leaves_out))
+        q = 10_000_000
+        gen = torch.Generator(device="cuda").manual_seed(args.seed)
+        idx = torch.randint(0, n0, (q,), device="cuda", dtype=torch.int64, generator=gen)
+        got = torch.empty(q, dtype=torch.int64, device="cuda")
+        ra_ms, _ = timed(lambda: tree.random_access(idx, out=got), reps=3)
+        ra_ok = bool(torch.equal(got, leaves_out[idx]))
+        del leaves_out, idx, got, dag
+        pipeline = {
+            "sort_tree_ms": round(sort_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
+            "stream_bytes": int(stream_bytes), "bits_per_base": round(8.0 * stream_bytes / bases_used, 4),
+            "serialize_gbs": round(stream_bytes / (ser_ms * 1e-3) / 1e9, 1),
+            "decode_ascii_ms": round(dec_ms, 3), "decode_ascii_gbp_s": round(bases_used / (dec_ms * 1e-3) / 1e9, 1),
+            "decode_leaves_ms": round(decl_ms, 3), "decode_roundtrip_equal": roundtrip_ok,
+            "random_access_queries": q, "random_access_ms": round(ra_ms, 3),
+            "random_access_mq_s": round(q / (ra_ms * 1e-3) / 1e6, 1), "random_access_equal": ra_ok,
+        }
+
     cpu = None
     if not args.no_cpu_baseline:
         sample = args.cpu_sample_bases or 120_000_000
@@ -302,7 +344,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
+        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "pipeline": pipeline,
         "tree": {"width": n0, "leaves": tree.leaf_count(), "nodes": tree.node_count(), "depth": tree.depth()},
     }
     print(json.dumps(line), flush=True)
