@@ -468,6 +468,85 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
   }
 }
 
+// ---- the small top of the tree in ONE launch ----------------------------------------------
+// Once a level has at most SMALL_MAX pointers, every remaining level (about a dozen) runs inside
+// a single CTA: pointers ping-pong in shared memory, the hash table lives in shared memory, and
+// __syncthreads() replaces the ~5 launches per level of the general path.
+constexpr uint32_t SMALL_MAX = 2048;        // pointers entering the kernel (<= 1024 positions per level)
+constexpr uint32_t SMALL_SLOTS = 2048;      // shared-memory table slots (load <= 0.5)
+constexpr int SMALL_MAX_LEVELS = 16;
+
+struct SmallOut {
+  uint2* nodes[SMALL_MAX_LEVELS];  // layer buffers of the levels this launch will build
+};
+
+__global__ void __launch_bounds__(1024)
+small_levels_kernel(const uint32_t* __restrict__ cur_in, uint32_t n_cur, SmallOut out, uint32_t* __restrict__ counts,
+                    uint32_t* __restrict__ root_out) {
+  __shared__ uint32_t ptr_a[SMALL_MAX], ptr_b[SMALL_MAX / 2];
+  __shared__ unsigned long long skey[SMALL_SLOTS];
+  __shared__ uint32_t smin[SMALL_SLOTS];
+  __shared__ uint32_t warp_cnt[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < n_cur; i += 1024) ptr_a[i] = cur_in[i];
+  uint32_t* cur = ptr_a;
+  uint32_t* nxt = ptr_b;
+  int level = 0;
+  do {
+    const uint32_t n_next = (n_cur + 1) / 2;
+    for (uint32_t i = tid; i < SMALL_SLOTS; i += 1024) {
+      skey[i] = EMPTY_KEY;
+      smin[i] = 0xffffffffu;
+    }
+    __syncthreads();
+    uint32_t cl = 0, cr = 0, f = 0, slot = 0;
+    const bool active = tid < n_next;
+    if (active) {
+      const uint32_t l = cur[2 * tid];
+      const uint32_t r = 2 * tid + 1 < n_cur ? cur[2 * tid + 1] : PTR_NULL;
+      canonical_node(l, r, cl, cr, f);
+      const unsigned long long key = ((unsigned long long)cl << 32) | cr;
+      slot = hash64(key) & (SMALL_SLOTS - 1);
+      for (;;) {
+        const unsigned long long old = atomicCAS(&skey[slot], EMPTY_KEY, key);
+        if (old == EMPTY_KEY || old == key) break;
+        slot = (slot + 1) & (SMALL_SLOTS - 1);
+      }
+      atomicMin(&smin[slot], tid);
+    }
+    __syncthreads();
+    const bool first = active && smin[slot] == tid;
+    const uint32_t word = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) warp_cnt[warp] = __popc(word);
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t v = warp_cnt[lane];
+      uint32_t x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+      }
+      warp_cnt[lane] = x - v;
+      if (lane == 31) counts[level] = x;
+    }
+    __syncthreads();
+    if (first) {
+      const uint32_t id = warp_cnt[warp] + __popc(word & ((1u << lane) - 1u));
+      out.nodes[level][id] = make_uint2(cl, cr);
+      nxt[tid] = finish_pointer(id, f);
+    }
+    __syncthreads();
+    if (active && !first) nxt[tid] = finish_pointer(nxt[smin[slot]] & IDX_MASK, f);
+    __syncthreads();
+    // the next level reads what this one wrote
+    if (cur == ptr_a) { cur = ptr_b; nxt = ptr_a; } else { cur = ptr_a; nxt = ptr_b; }
+    n_cur = n_next;
+    ++level;
+  } while (n_cur > 1);
+  if (tid == 0) *root_out = cur[0];
+}
+
 // Tunables of the partitioned path (environment overrides are for experiments only).
 static uint64_t env_u64(const char* name, uint64_t fallback) {
   const char* v = getenv(name);
@@ -483,6 +562,23 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
   cudaStream_t st = t.stream;
   int level = 0;
   do {
+    if (n_cur <= SMALL_MAX) {  // the rest of the tree in one launch
+      SmallOut out{};
+      int extra = 0;
+      for (uint64_t n = n_cur;;) {
+        n = ceil_div(n, 2);
+        t.layers.emplace_back();
+        STB_CUDA(t, t.layers.back().nodes.alloc(n, st));
+        out.nodes[extra++] = t.layers.back().nodes.ptr;
+        if (n <= 1) break;
+      }
+      if (!sc.root.ptr) STB_CUDA(t, sc.root.alloc(1, st));
+      Launch l(t, "small_levels");
+      small_levels_kernel<<<1, 1024, 0, st>>>(cur, (uint32_t)n_cur, out, counts_dev + level, sc.root.ptr);
+      level += extra;
+      cur = sc.root.ptr;
+      break;
+    }
     const uint64_t n_next = ceil_div(n_cur, 2);
     t.layers.emplace_back();
     Layer& layer = t.layers.back();
