@@ -229,13 +229,24 @@ __device__ __forceinline__ uint32_t tagged_insert(Slot* tab, uint32_t cap, unsig
   }
 }
 
-// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
-__global__ void __launch_bounds__(LVL_THREADS)
-node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
-                   const uint32_t* __restrict__ child_unique, uint32_t serial) {
-  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
-  if (p >= n_next) return;
-  uint32_t l, r;
+// Singleton filter for the first node layer (its keys are pairs of leaf ids: no locality to
+// exploit, so every table access is a random HBM line).  Two bit planes that fit in L2: plane A
+// = "some position hashed here", plane B = "at least two did".  A position whose B bit stays
+// clear shares its filter cell with nobody, so its key occurs exactly once in the level: it is
+// a first occurrence that nobody will ever look up, and it skips the table altogether.
+struct SingletonFilter {
+  uint32_t* plane_a = nullptr;
+  uint32_t* plane_b = nullptr;
+  uint32_t log2_bits = 0;
+};
+
+__device__ __forceinline__ void filter_cell(const SingletonFilter& flt, unsigned long long key, uint32_t& word, uint32_t& bit) {
+  const uint32_t h = (uint32_t)mix64(key) >> (32 - flt.log2_bits);  // low half of the mix: the table uses the high half
+  word = h >> 5;
+  bit = 1u << (h & 31);
+}
+
+__device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p, uint32_t& l, uint32_t& r) {
   if (2 * (uint64_t)p + 1 < n_cur) {
     const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
     l = pr.x;
@@ -244,9 +255,38 @@ node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
     l = cur[2 * (uint64_t)p];
     r = PTR_NULL;
   }
+}
+
+__global__ void __launch_bounds__(LVL_THREADS)
+node_filter_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, SingletonFilter flt) {
+  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= n_next) return;
+  uint32_t l, r, cl, cr, f, word, bit;
+  load_children(cur, n_cur, p, l, r);
+  canonical_node(l, r, cl, cr, f);
+  filter_cell(flt, ((unsigned long long)cl << 32) | cr, word, bit);
+  if (atomicOr(flt.plane_a + word, bit) & bit) atomicOr(flt.plane_b + word, bit);
+}
+
+// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
+__global__ void __launch_bounds__(LVL_THREADS)
+node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
+                   const uint32_t* __restrict__ child_unique, uint32_t serial, SingletonFilter flt) {
+  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  if (p >= n_next) return;
+  uint32_t l, r;
+  load_children(cur, n_cur, p, l, r);
   uint32_t cl, cr, f;
   canonical_node(l, r, cl, cr, f);
   const unsigned long long key = ((unsigned long long)cl << 32) | cr;
+  if (flt.plane_b) {
+    uint32_t word, bit;
+    filter_cell(flt, key, word, bit);
+    if (!(__ldcg(flt.plane_b + word) & bit)) {  // the only position with this key
+      atomicOr(tab.first_bits + (p >> 5), 1u << (p & 31));
+      return;  // assign_kernel recomputes the node; nobody resolves through tmp[p]
+    }
+  }
   const uint32_t hashed = __umulhi(hash64(key), tab.cap);
   uint32_t start = hashed, limit = 0xffffffffu;
   if (child_unique) {
@@ -426,8 +466,9 @@ struct Scratch {
   DevBuf<Slot> slots;
   DevBuf<BuildFlags> flags;
   DevBuf<uint32_t> root;
-  bool tags_cleared = false;  // partitioned levels: slots carry an epoch tag, cleared once per build
+  bool tags_cleared = false;  // node tables: slots carry an epoch tag, cleared once per build
   uint32_t serial = 0;
+  DevBuf<uint32_t> filter;    // singleton filter of the first node layer (two bit planes)
 };
 
 uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
@@ -553,6 +594,14 @@ static uint64_t env_u64(const char* name, uint64_t fallback) {
   return v ? strtoull(v, nullptr, 0) : fallback;
 }
 
+// words of the two filter planes for a first node layer of n positions (0 = filter not used)
+static uint64_t filter_words(uint64_t n) {
+  if (n < env_u64("STB_FILTER_MIN", 1ull << 22)) return 0;
+  uint32_t log2_bits = 22;
+  while (log2_bits < 28 && (1ull << log2_bits) < 2 * n) ++log2_bits;
+  return 2 * ((1ull << log2_bits) / 32);
+}
+
 // Node levels from a pointer array down to a single root pointer.  Appends one layer per
 // level to t.layers; counts_dev[level] receives each layer's size; returns the buffer that
 // holds the root pointer in *root_buf.
@@ -593,6 +642,20 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       sc.tags_cleared = true;
     }
     STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n_next, LVL_TILE) * (LVL_TILE / 8), st));
+    SingletonFilter flt;
+    static const uint64_t filter_min = env_u64("STB_FILTER_MIN", 1ull << 22);
+    if (level == 0 && n_next >= filter_min) {
+      // two planes of 2^k bits, k as large as keeps both in L2 (<= 2 x 32 MiB)
+      flt.log2_bits = 22;
+      while (flt.log2_bits < 28 && (1ull << flt.log2_bits) < 2 * n_next) ++flt.log2_bits;
+      const uint64_t words = (1ull << flt.log2_bits) / 32;
+      if (sc.filter.count < 2 * words) STB_CUDA(t, sc.filter.alloc(2 * words, st));  // normally pre-allocated with the scratch
+      STB_CUDA(t, cudaMemsetAsync(sc.filter.ptr, 0, 2 * words * 4, st));
+      flt.plane_a = sc.filter.ptr;
+      flt.plane_b = sc.filter.ptr + words;
+      Launch l(t, "node_filter");
+      node_filter_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, flt);
+    }
     {
       // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
       // and chunking the level to keep table lines in L2 did not pay (profiles/README.md).
@@ -600,7 +663,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       // children of level 0 are leaf ids (or an imported array): not position-ordered
       const uint32_t* child_unique = (locality && level > 0) ? counts_dev + level - 1 : nullptr;
       node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
-                                                                                          ++sc.serial);
+                                                                                          ++sc.serial, flt);
     }
     finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
     std::swap(cur, nxt);
@@ -624,6 +687,7 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   STB_CUDA(t, sc.counts.alloc(80, st));
   STB_CUDA(t, sc.flags.alloc(1, st));
   STB_CUDA(t, sc.root.alloc(1, st));
+  STB_CUDA(t, sc.filter.alloc(filter_words(n1), st));
   {
     BuildFlags init{~0ull, 0u, 0u};
     STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));

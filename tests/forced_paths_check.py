@@ -1,0 +1,43 @@
+"""Run in a subprocess with STB_FILTER_MIN=1, so that the singleton filter of the first node
+layer (normally only used from 4M positions up) handles inputs small enough for the oracle."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from conftest import corpus_text, load_package  # noqa: E402
+from oracle.pyoracle import Oracle  # noqa: E402
+
+
+def main():
+    import torch
+    stb, oracle = load_package(), Oracle()
+    for name, S in (("merged", 12), ("humhbb", 5), ("vaccg", 16), ("chmpxx", 1)):
+        text = corpus_text(name)
+        leaves = oracle.fasta_to_leaves(text, S)
+        got, want = stb.SharedTree(S).build_from_fasta(text), oracle.build(leaves, S)
+        assert got.layer_counts() == want.layer_counts(), (name, S)
+        assert got.serialize() == want.serialize(), (name, S)
+        got.sort(); want.sort()
+        assert got.serialize() == want.serialize(), (name, S)
+        assert np.array_equal(got.decode(), leaves)
+    n = 7_000_000
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(buf, n, seed=11, repeat_permille=500)
+    leaves = oracle.fasta_to_leaves(buf.cpu().numpy().tobytes(), 12)
+    got, want = stb.SharedTree(12).build_from_body(buf), oracle.build(leaves, 12)
+    assert got.serialize() == want.serialize()
+    rng = np.random.default_rng(5)
+    codes = np.array([1, 2, 4, 8, 3, 12, 7, 14, 0, 9, 5, 11, 13, 10, 6, 15], dtype=np.uint64)
+    nib = codes[rng.integers(0, 16, size=(40000, 12))]
+    lv = (nib << (4 * np.arange(12, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+    lv[20000:30000] = lv[:10000]
+    assert stb.SharedTree(12).build_from_leaves(lv).serialize() == oracle.build(lv, 12).serialize()
+    print("forced_paths_check ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()
