@@ -61,6 +61,7 @@ def _load() -> C.CDLL:
         "stb_create": [P(vp), i32, i32, vp],
         "stb_destroy": [vp],
         "stb_clone": [vp, P(vp)],
+        "stb_release_workspace": [vp],
         "stb_build_from_fasta": [vp, vp, u64, i32],
         "stb_build_from_body": [vp, vp, u64, i32],
         "stb_build_from_leaves": [vp, vp, u64, i32],

@@ -466,10 +466,22 @@ struct Scratch {
   DevBuf<Slot> slots;
   DevBuf<BuildFlags> flags;
   DevBuf<uint32_t> root;
-  bool tags_cleared = false;  // node tables: slots carry an epoch tag, cleared once per build
+  // Node tables: a slot's last word is an epoch tag; every node level of every build on this
+  // handle takes a fresh serial, so the table is cleared only when its memory is new.
+  bool tags_cleared = false;
   uint32_t serial = 0;
   DevBuf<uint32_t> filter;    // singleton filter of the first node layer (two bit planes)
 };
+
+Scratch& workspace_of(Tree& t) {
+  if (!t.workspace) t.workspace = std::make_shared<Scratch>();
+  Scratch& sc = *static_cast<Scratch*>(t.workspace.get());
+  if (sc.serial > 0xfff00000u) {  // far from wrapping into a tag that is still in the table
+    sc.serial = 0;
+    sc.tags_cleared = false;
+  }
+  return sc;
+}
 
 uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
 
@@ -621,7 +633,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
         out.nodes[extra++] = t.layers.back().nodes.ptr;
         if (n <= 1) break;
       }
-      if (!sc.root.ptr) STB_CUDA(t, sc.root.alloc(1, st));
+      STB_CUDA(t, sc.root.ensure(1, st));
       Launch l(t, "small_levels");
       small_levels_kernel<<<1, 1024, 0, st>>>(cur, (uint32_t)n_cur, out, counts_dev + level, sc.root.ptr);
       level += extra;
@@ -640,6 +652,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       Launch l(t, "table_clear", false);
       STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, sc.slots.bytes(), st));
       sc.tags_cleared = true;
+      sc.serial = 0;
     }
     STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n_next, LVL_TILE) * (LVL_TILE / 8), st));
     SingletonFilter flt;
@@ -649,7 +662,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       flt.log2_bits = 22;
       while (flt.log2_bits < 28 && (1ull << flt.log2_bits) < 2 * n_next) ++flt.log2_bits;
       const uint64_t words = (1ull << flt.log2_bits) / 32;
-      if (sc.filter.count < 2 * words) STB_CUDA(t, sc.filter.alloc(2 * words, st));  // normally pre-allocated with the scratch
+      STB_CUDA(t, sc.filter.ensure(2 * words, st));  // already there: sized with the rest of the workspace
       STB_CUDA(t, cudaMemsetAsync(sc.filter.ptr, 0, 2 * words * 4, st));
       flt.plane_a = sc.filter.ptr;
       flt.plane_b = sc.filter.ptr + words;
@@ -678,16 +691,16 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
 int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   const int S = t.S;
   cudaStream_t st = t.stream;
-  Scratch sc;
+  Scratch& sc = workspace_of(t);
   const uint64_t n1 = ceil_div(n0, 2);
-  STB_CUDA(t, sc.ptr_a.alloc(n0, st));
-  STB_CUDA(t, sc.ptr_b.alloc(n1, st));
-  STB_CUDA(t, sc.bitmask.alloc(ceil_div(n0, LVL_TILE) * (LVL_TILE / 32), st));
-  STB_CUDA(t, sc.blockcnt.alloc(ceil_div(n0, LVL_TILE) + 1, st));
-  STB_CUDA(t, sc.counts.alloc(80, st));
-  STB_CUDA(t, sc.flags.alloc(1, st));
-  STB_CUDA(t, sc.root.alloc(1, st));
-  STB_CUDA(t, sc.filter.alloc(filter_words(n1), st));
+  STB_CUDA(t, sc.ptr_a.ensure(n0, st));
+  STB_CUDA(t, sc.ptr_b.ensure(n1, st));
+  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n0, LVL_TILE) * (LVL_TILE / 32), st));
+  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n0, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.counts.ensure(80, st));
+  STB_CUDA(t, sc.flags.ensure(1, st));
+  STB_CUDA(t, sc.root.ensure(1, st));
+  STB_CUDA(t, sc.filter.ensure(filter_words(n1), st));
   {
     BuildFlags init{~0ull, 0u, 0u};
     STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -697,13 +710,17 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   const uint64_t direct_entries = direct ? (1ull << (2 * S)) : 0;
   const uint32_t leaf_cap = direct ? 0u : table_cap(n0);
   const uint32_t node_cap_max = table_cap(n1);
-  STB_CUDA(t, sc.slots.alloc((uint64_t)std::max(leaf_cap, node_cap_max) + 1, st));
+  {
+    bool grew = false;
+    STB_CUDA(t, sc.slots.ensure((uint64_t)std::max(leaf_cap, node_cap_max) + 1, st, &grew));
+    if (grew) sc.tags_cleared = false;
+  }
   LevelTable tab{sc.slots.ptr, nullptr, nullptr, leaf_cap};
   tab.first_bits = sc.bitmask.ptr;
-  STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, sc.bitmask.bytes(), st));
+  STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n0, LVL_TILE) * (LVL_TILE / 8), st));
   if (direct) {
-    STB_CUDA(t, sc.dminpos.alloc(direct_entries, st));
-    STB_CUDA(t, sc.dids.alloc(direct_entries, st));
+    STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
+    STB_CUDA(t, sc.dids.ensure(direct_entries, st));
     tab.dminpos = sc.dminpos.ptr;
     tab.dids = sc.dids.ptr;
     Launch l(t, "table_clear", false);
@@ -821,14 +838,19 @@ int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_leas
     t.built = true;
     return STB_OK;
   }
-  Scratch sc;
+  Scratch& sc = workspace_of(t);
   const uint64_t n1 = ceil_div(n, 2);
-  STB_CUDA(t, sc.ptr_a.alloc(n, st));
-  STB_CUDA(t, sc.ptr_b.alloc(n1, st));
-  STB_CUDA(t, sc.bitmask.alloc(ceil_div(n1, LVL_TILE) * (LVL_TILE / 32), st));
-  STB_CUDA(t, sc.blockcnt.alloc(ceil_div(n1, LVL_TILE) + 1, st));
-  STB_CUDA(t, sc.counts.alloc(80, st));
-  STB_CUDA(t, sc.slots.alloc((uint64_t)table_cap(n1) + 1, st));
+  STB_CUDA(t, sc.ptr_a.ensure(n, st));
+  STB_CUDA(t, sc.ptr_b.ensure(n1, st));
+  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n1, LVL_TILE) * (LVL_TILE / 32), st));
+  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n1, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.counts.ensure(80, st));
+  STB_CUDA(t, sc.filter.ensure(filter_words(n1), st));
+  {
+    bool grew = false;
+    STB_CUDA(t, sc.slots.ensure((uint64_t)table_cap(n1) + 1, st, &grew));
+    if (grew) sc.tags_cleared = false;
+  }
   STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, d_ptrs, n * 4, cudaMemcpyDeviceToDevice, st));
   int level = 0;
   uint32_t* cur = nullptr;

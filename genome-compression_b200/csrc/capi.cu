@@ -90,13 +90,16 @@ int to_device(Tree& t, const T* src, uint64_t count, int memory, DevBuf<T>& hold
     *out = src;
     return STB_OK;
   }
-  STB_CUDA(t, hold.alloc(count + 16 / sizeof(T), t.stream));
+  // the handle's grow-only staging buffer: no device allocation per call in steady state
+  (void)hold;
+  STB_CUDA(t, t.staging.ensure(count * sizeof(T) + 16, t.stream));
+  T* dst = reinterpret_cast<T*>(t.staging.ptr);
   if (count) {
     Launch l(t, memory == STB_HOST ? "h2d_copy" : "d2d_copy", false);
-    STB_CUDA(t, cudaMemcpyAsync(hold.ptr, src, count * sizeof(T),
+    STB_CUDA(t, cudaMemcpyAsync(dst, src, count * sizeof(T),
                                 memory == STB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, t.stream));
   }
-  *out = hold.ptr;
+  *out = dst;
   return STB_OK;
 }
 
@@ -138,10 +141,20 @@ int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream) {
   return STB_OK;
 }
 
+int stb_release_workspace(stb_tree* tree) {
+  if (!tree) return STB_ERR_INVALID_ARG;
+  STB_TRY(use_device(tree));
+  tree->workspace.reset();
+  tree->staging.release();
+  return STB_OK;
+}
+
 int stb_destroy(stb_tree* tree) {
   if (!tree) return STB_OK;
   cudaSetDevice(tree->device);
   tree->clear();
+  tree->workspace.reset();
+  tree->staging.release();
   cudaStreamSynchronize(tree->stream);
   delete tree;
   return STB_OK;

@@ -351,6 +351,14 @@ struct DevBuf {
     if (n == 0) n = 1;
     return cudaMallocAsync((void**)&ptr, n * sizeof(T), s);
   }
+  // grow-only: keeps the current block when it is already large enough; *grew tells the caller
+  // that the contents are new (uninitialised) memory
+  cudaError_t ensure(uint64_t n, cudaStream_t s, bool* grew = nullptr) {
+    if (grew) *grew = false;
+    if (ptr && count >= n) return cudaSuccess;
+    if (grew) *grew = true;
+    return alloc(n, s);
+  }
   void release() {
     if (ptr) cudaFreeAsync(ptr, stream);
     ptr = nullptr;

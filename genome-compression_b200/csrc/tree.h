@@ -1,6 +1,8 @@
 // tree.h — device-resident shared_tree and the internal entry points of each stage.
 #pragma once
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace stb {
@@ -21,6 +23,12 @@ struct Tree : Ctx {
   std::vector<Layer> layers;
   uint32_t root = PTR_NULL;
   uint64_t width = 0;
+
+  // Build workspace (pointer arrays, tables, bitmaps: build.cu's Scratch) and the host-input
+  // staging buffer.  Both are grow-only and live until stb_destroy / stb_release_workspace, so
+  // repeated builds on one handle do no device allocation.
+  std::shared_ptr<void> workspace;
+  DevBuf<char> staging;
 
   // serialization plan cache (per-layer byte totals), invalidated by build / sort
   bool plan_valid = false;

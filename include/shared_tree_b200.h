@@ -59,6 +59,9 @@ enum stb_memory { STB_HOST = 0, STB_DEVICE = 1 };
 int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream);
 int stb_destroy(stb_tree* tree);
 int stb_clone(const stb_tree* tree, stb_tree** out);
+/* A handle keeps its build workspace (tables, pointer arrays, host-input staging) between
+ * builds so that repeated builds allocate nothing; this gives it back early. */
+int stb_release_workspace(stb_tree* tree);
 
 /* ---- construction --------------------------------------------------------- */
 /* shared_tree(fasta_reader, bool), src/shared_tree.cpp:207 + the ingest semantics
