@@ -259,20 +259,25 @@ __device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, 
 
 __global__ void __launch_bounds__(LVL_THREADS)
 node_filter_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, SingletonFilter flt) {
-  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
-  if (p >= n_next) return;
-  uint32_t l, r, cl, cr, f, word, bit;
-  load_children(cur, n_cur, p, l, r);
-  canonical_node(l, r, cl, cr, f);
-  filter_cell(flt, ((unsigned long long)cl << 32) | cr, word, bit);
-  if (atomicOr(flt.plane_a + word, bit) & bit) atomicOr(flt.plane_b + word, bit);
+#pragma unroll
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    if (p >= n_next) return;
+    uint32_t l, r, cl, cr, f, word, bit;
+    load_children(cur, n_cur, p, l, r);
+    canonical_node(l, r, cl, cr, f);
+    filter_cell(flt, ((unsigned long long)cl << 32) | cr, word, bit);
+    if (atomicOr(flt.plane_a + word, bit) & bit) atomicOr(flt.plane_b + word, bit);
+  }
 }
 
 // One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
 __global__ void __launch_bounds__(LVL_THREADS)
 node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
                    const uint32_t* __restrict__ child_unique, uint32_t serial, SingletonFilter flt) {
-  const uint32_t p = blockIdx.x * LVL_THREADS + threadIdx.x;
+  // several positions per thread: CTAs that live for one probe each are dispatch-bound
+  for (int it = 0; it < LVL_ITERS; ++it) {
+  const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
   if (p >= n_next) return;
   uint32_t l, r;
   load_children(cur, n_cur, p, l, r);
@@ -284,7 +289,7 @@ node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
     filter_cell(flt, key, word, bit);
     if (!(__ldcg(flt.plane_b + word) & bit)) {  // the only position with this key
       atomicOr(tab.first_bits + (p >> 5), 1u << (p & 31));
-      return;  // assign_kernel recomputes the node; nobody resolves through tmp[p]
+      continue;  // assign_kernel recomputes the node; nobody resolves through tmp[p]
     }
   }
   const uint32_t hashed = __umulhi(hash64(key), tab.cap);
@@ -295,12 +300,13 @@ node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
     // probe neighbouring slots (one 128-byte line serves several positions instead of one line
     // per position).  Crowded neighbourhoods (one child with many partners) fall back to the hash.
     const uint32_t child = ptr_is_null(cl) ? (cr & IDX_MASK) : (cl & IDX_MASK);
-    const uint32_t unique = max(1u, __ldg(child_unique));
-    start = (uint32_t)(((unsigned long long)child * tab.cap) / unique) + (hashed & 7u);
-    if (start >= tab.cap) start = tab.cap - 1;
+    // (any deterministic function of the key will do: single-precision scaling, no 64-bit divide)
+    const float ratio = __fdividef((float)tab.cap, (float)max(1u, __ldg(child_unique)));
+    start = (uint32_t)min((float)(tab.cap - 9u), (float)child * ratio) + (hashed & 7u);
     limit = 24u;
   }
   tmp[p] = tagged_insert(tab.slots, tab.cap, key, p, serial, start, hashed, limit, tab.first_bits) | f;
+  }
 }
 
 // per-CTA first-occurrence counts (LVL_TILE positions = 32 bitmask words) for the scan
@@ -659,15 +665,16 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     static const uint64_t filter_min = env_u64("STB_FILTER_MIN", 1ull << 22);
     if (level == 0 && n_next >= filter_min) {
       // two planes of 2^k bits, k as large as keeps both in L2 (<= 2 x 32 MiB)
+      static const uint32_t max_log2 = (uint32_t)env_u64("STB_FILTER_LOG2", 28);
       flt.log2_bits = 22;
-      while (flt.log2_bits < 28 && (1ull << flt.log2_bits) < 2 * n_next) ++flt.log2_bits;
+      while (flt.log2_bits < max_log2 && (1ull << flt.log2_bits) < 2 * n_next) ++flt.log2_bits;
       const uint64_t words = (1ull << flt.log2_bits) / 32;
       STB_CUDA(t, sc.filter.ensure(2 * words, st));  // already there: sized with the rest of the workspace
       STB_CUDA(t, cudaMemsetAsync(sc.filter.ptr, 0, 2 * words * 4, st));
       flt.plane_a = sc.filter.ptr;
       flt.plane_b = sc.filter.ptr + words;
       Launch l(t, "node_filter");
-      node_filter_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, flt);
+      node_filter_kernel<<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, flt);
     }
     {
       // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
@@ -675,7 +682,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       Launch l(t, "node_insert");
       // children of level 0 are leaf ids (or an imported array): not position-ordered
       const uint32_t* child_unique = (locality && level > 0) ? counts_dev + level - 1 : nullptr;
-      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_THREADS), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
+      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
                                                                                           ++sc.serial, flt);
     }
     finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
