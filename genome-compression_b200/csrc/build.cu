@@ -274,10 +274,10 @@ node_filter_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
 // One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
 __global__ void __launch_bounds__(LVL_THREADS)
 node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
-                   const uint32_t* __restrict__ child_unique, uint32_t serial, SingletonFilter flt) {
+                   const uint32_t* __restrict__ child_unique, uint32_t serial, SingletonFilter flt, uint32_t first_block) {
   // several positions per thread: CTAs that live for one probe each are dispatch-bound
   for (int it = 0; it < LVL_ITERS; ++it) {
-  const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+  const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
   if (p >= n_next) return;
   uint32_t l, r;
   load_children(cur, n_cur, p, l, r);
@@ -325,11 +325,11 @@ bitmask_blockcnt_kernel(const uint32_t* __restrict__ bitmask, uint32_t n_blocks,
 // round); total -> *total_out.
 constexpr int SCAN_PER_THREAD = 16;
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ cnt, uint32_t nb,
-                                                           uint32_t* __restrict__ total_out) {
+                                                           uint32_t* total_out, const uint32_t* carry_in) {
   __shared__ uint32_t warp_sum[32];
   __shared__ uint32_t carry_s;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  if (threadIdx.x == 0) carry_s = carry_in ? *carry_in : 0u;  // streaming build: ids continue where the last chunk stopped
   __syncthreads();
   for (uint32_t base = 0; base < nb; base += 1024 * SCAN_PER_THREAD) {
     const uint32_t i0 = base + threadIdx.x * SCAN_PER_THREAD;
@@ -380,13 +380,14 @@ template <int MODE>
 __global__ void __launch_bounds__(LVL_THREADS)
 assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
               const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S,
-              const uint32_t* __restrict__ children, uint32_t n_children) {
+              const uint32_t* __restrict__ children, uint32_t n_children, uint32_t first_block) {
   __shared__ uint32_t word_pref[32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t block = first_block + blockIdx.x;
   uint32_t words[LVL_ITERS];
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p0 = blockIdx.x * LVL_TILE + it * LVL_THREADS + warp * 32;
+    const uint32_t p0 = block * LVL_TILE + it * LVL_THREADS + warp * 32;
     words[it] = p0 < n ? bitmask[p0 >> 5] : 0u;
     if (lane == 0) word_pref[it * (LVL_THREADS / 32) + warp] = __popc(words[it]);
   }
@@ -402,10 +403,10 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
     word_pref[lane] = x - v;
   }
   __syncthreads();
-  const uint32_t base = blockbase[blockIdx.x];
+  const uint32_t base = blockbase[block];
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
     if (p < n && ((words[it] >> lane) & 1u)) {
       const uint32_t rank = base + word_pref[it * (LVL_THREADS / 32) + warp] + __popc(words[it] & ((1u << lane) - 1u));
       const uint32_t t = MODE == MODE_NODE ? 0u : tmp[p];
@@ -440,11 +441,11 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
 // left in tmp[p].
 template <bool DIRECT>
 __global__ void __launch_bounds__(LVL_THREADS)
-resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask) {
+resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask, uint32_t first_block) {
   const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
     if (p < n) {
       const uint32_t word = bitmask[p >> 5];
       if (!((word >> lane) & 1u)) {
@@ -477,6 +478,17 @@ struct Scratch {
   bool tags_cleared = false;
   uint32_t serial = 0;
   DevBuf<uint32_t> filter;    // singleton filter of the first node layer (two bit planes)
+
+  // streaming build (host input): every chunked level keeps its own pointer array, bitmap,
+  // per-CTA counts and table for the whole build
+  DevBuf<uint32_t> ptr_arena, bit_arena, cnt_arena, level_sizes;
+  DevBuf<Slot> stream_slots;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  ~Scratch() {
+    for (auto e : chunk_events) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
 };
 
 Scratch& workspace_of(Tree& t) {
@@ -515,15 +527,15 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
   }
   {
     Launch l(ctx, "scan_blocks");
-    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, total_out);
+    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, total_out, nullptr);
   }
   {
     Launch l(ctx, "assign_ids");
-    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children);
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children, 0u);
   }
   {
     Launch l(ctx, "resolve_ids");
-    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr);
+    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, 0u);
   }
 }
 
@@ -683,7 +695,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       // children of level 0 are leaf ids (or an imported array): not position-ordered
       const uint32_t* child_unique = (locality && level > 0) ? counts_dev + level - 1 : nullptr;
       node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
-                                                                                          ++sc.serial, flt);
+                                                                                          ++sc.serial, flt, 0u);
     }
     finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
     std::swap(cur, nxt);
@@ -692,6 +704,61 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
   } while (n_cur > 1);
   *levels_out = level;
   *root_buf = cur;
+  return STB_OK;
+}
+
+// Reads back the per-layer counts, the flags and the root; fills in the tree; trims storage.
+int finish_build(Tree& t, Scratch& sc, uint64_t n0, int level, const uint32_t* cur, bool direct) {
+  cudaStream_t st = t.stream;
+  std::vector<uint32_t> counts(level + 1);
+  BuildFlags flags{};
+  uint32_t root = PTR_NULL;
+  STB_CUDA(t, cudaMemcpyAsync(counts.data(), sc.counts.ptr, counts.size() * 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(&flags, sc.flags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(&root, cur, 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaStreamSynchronize(st));
+  STB_CUDA(t, cudaGetLastError());
+
+  if (flags.bad_symbol != ~0ull) {
+    t.clear();
+    return t.fail(STB_ERR_UNKNOWN_SYMBOL, unknown_symbol_message((int)(flags.bad_symbol & 0xff)));
+  }
+  if (flags.bad_leaf) {
+    t.clear();
+    return t.fail(STB_ERR_BAD_LEAF, "packed leaf has bits set at or above 4*dna_size");
+  }
+  if (direct && flags.non_acgt) {
+    t.clear();
+    return -1;  // caller retries with the hash-table leaf level
+  }
+  for (uint32_t c : counts)
+    if (c >= IDX_MASK) {
+      t.clear();
+      return t.fail(STB_ERR_INDEX_CEILING, "a layer has 2^29-1 or more unique items; the pointer format cannot index it");
+    }
+
+  t.n_leaves = counts[0];
+  for (int k = 0; k < level; ++k) t.layers[k].count = counts[k + 1];
+  t.root = root;
+  t.width = n0;
+  t.built = true;
+  t.plan_valid = false;
+
+  // Give back over-provisioned storage (worst case was one item per position).
+  if (t.n_leaves * 2 < t.leaves.count) {
+    DevBuf<unsigned long long> exact;
+    STB_CUDA(t, exact.alloc(t.n_leaves, st));
+    STB_CUDA(t, cudaMemcpyAsync(exact.ptr, t.leaves.ptr, t.n_leaves * 8, cudaMemcpyDeviceToDevice, st));
+    t.leaves = std::move(exact);
+  }
+  for (auto& layer : t.layers) {
+    if (layer.count * 2 < layer.nodes.count) {
+      DevBuf<uint2> exact;
+      STB_CUDA(t, exact.alloc(layer.count, st));
+      STB_CUDA(t, cudaMemcpyAsync(exact.ptr, layer.nodes.ptr, layer.count * 8, cudaMemcpyDeviceToDevice, st));
+      layer.nodes = std::move(exact);
+    }
+  }
   return STB_OK;
 }
 
@@ -763,56 +830,159 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n0, sc.counts.ptr + 1, &level, &cur));
   // `cur` now holds the single root pointer.
 
-  std::vector<uint32_t> counts(level + 1);
-  BuildFlags flags{};
-  uint32_t root = PTR_NULL;
-  STB_CUDA(t, cudaMemcpyAsync(counts.data(), sc.counts.ptr, counts.size() * 4, cudaMemcpyDeviceToHost, st));
-  STB_CUDA(t, cudaMemcpyAsync(&flags, sc.flags.ptr, sizeof(flags), cudaMemcpyDeviceToHost, st));
-  STB_CUDA(t, cudaMemcpyAsync(&root, cur, 4, cudaMemcpyDeviceToHost, st));
-  STB_CUDA(t, cudaStreamSynchronize(st));
-  STB_CUDA(t, cudaGetLastError());
+  return finish_build(t, sc, n0, level, cur, direct);
+}
 
-  if (flags.bad_symbol != ~0ull) {
-    t.clear();
-    return t.fail(STB_ERR_UNKNOWN_SYMBOL, unknown_symbol_message((int)(flags.bad_symbol & 0xff)));
+// ---- streaming build from host memory --------------------------------------------------------
+// Ids are first-occurrence ranks in position order, and a later position can never displace an
+// earlier one, so once a chunk of positions has been inserted its first-occurrence bits and ids
+// are final.  The text is therefore copied in power-of-two chunks (the reference's own streaming
+// unit, include/shared_tree.h:305-316) and every chunk runs through all the levels it spans while
+// the next one is still on the PCIe bus; the scan of each level simply continues from the running
+// total.  Only the last chunk's work and the small top of the tree remain after the copy ends.
+int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
+  const int S = t.S;
+  const uint64_t n0 = body_len / (uint64_t)S;
+  static const int chunk_log2 = (int)env_u64("STB_STREAM_CHUNK_LOG2", 24);
+  static const uint64_t min_chunks = env_u64("STB_STREAM_MIN_CHUNKS", 4);
+  const uint64_t C = 1ull << chunk_log2;
+  if (S > 12 || chunk_log2 < 12 || n0 < min_chunks * C || n0 >= 0x7f000000ull) return -1;
+  const int Lc = chunk_log2 - 11;  // chunked node levels: a chunk still holds 2048 positions at the last one
+  cudaStream_t st = t.stream;
+  t.clear();
+  Scratch& sc = workspace_of(t);
+
+  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), cnt_off(Lc + 2, 0), slot_off(Lc + 2, 0);
+  n[0] = n0;
+  for (int j = 1; j <= Lc; ++j) n[j] = ceil_div(n[j - 1], 2);
+  for (int j = 0; j <= Lc; ++j) {
+    const uint64_t blocks = ceil_div(n[j], LVL_TILE);
+    ptr_off[j + 1] = ptr_off[j] + blocks * LVL_TILE;
+    bit_off[j + 1] = bit_off[j] + blocks * (LVL_TILE / 32);
+    cnt_off[j + 1] = cnt_off[j] + blocks + 1;
+    slot_off[j + 1] = slot_off[j] + (j == 0 ? 0 : (uint64_t)table_cap(n[j]) + 1);
   }
-  if (flags.bad_leaf) {
-    t.clear();
-    return t.fail(STB_ERR_BAD_LEAF, "packed leaf has bits set at or above 4*dna_size");
-  }
-  if (direct && flags.non_acgt) {
-    t.clear();
-    return -1;  // caller retries with the hash-table leaf level
-  }
-  for (uint32_t c : counts)
-    if (c >= IDX_MASK) {
-      t.clear();
-      return t.fail(STB_ERR_INDEX_CEILING, "a layer has 2^29-1 or more unique items; the pointer format cannot index it");
+  const uint64_t direct_entries = 1ull << (2 * S);
+  STB_CUDA(t, t.staging.ensure(n0 * (uint64_t)S + 16, st));
+  STB_CUDA(t, sc.ptr_arena.ensure(ptr_off[Lc + 1], st));
+  STB_CUDA(t, sc.bit_arena.ensure(bit_off[Lc + 1], st));
+  STB_CUDA(t, sc.cnt_arena.ensure(cnt_off[Lc + 1], st));
+  STB_CUDA(t, sc.level_sizes.ensure(Lc + 2, st));
+  STB_CUDA(t, sc.counts.ensure(80, st));
+  STB_CUDA(t, sc.flags.ensure(1, st));
+  STB_CUDA(t, sc.root.ensure(1, st));
+  STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
+  STB_CUDA(t, sc.dids.ensure(direct_entries, st));
+  {
+    bool grew = false;
+    STB_CUDA(t, sc.stream_slots.ensure(slot_off[Lc + 1], st, &grew));
+    if (grew) {
+      Launch l(t, "table_clear", false);
+      STB_CUDA(t, cudaMemsetAsync(sc.stream_slots.ptr, 0xff, sc.stream_slots.bytes(), st));
     }
-
-  t.n_leaves = counts[0];
-  for (int k = 0; k < level; ++k) t.layers[k].count = counts[k + 1];
-  t.root = root;
-  t.width = n0;
-  t.built = true;
-  t.plan_valid = false;
-
-  // Give back over-provisioned storage (worst case was one item per position).
-  if (t.n_leaves * 2 < t.leaves.count) {
-    DevBuf<unsigned long long> exact;
-    STB_CUDA(t, exact.alloc(t.n_leaves, st));
-    STB_CUDA(t, cudaMemcpyAsync(exact.ptr, t.leaves.ptr, t.n_leaves * 8, cudaMemcpyDeviceToDevice, st));
-    t.leaves = std::move(exact);
   }
-  for (auto& layer : t.layers) {
-    if (layer.count * 2 < layer.nodes.count) {
-      DevBuf<uint2> exact;
-      STB_CUDA(t, exact.alloc(layer.count, st));
-      STB_CUDA(t, cudaMemcpyAsync(exact.ptr, layer.nodes.ptr, layer.count * 8, cudaMemcpyDeviceToDevice, st));
-      layer.nodes = std::move(exact);
+  STB_CUDA(t, cudaMemsetAsync(sc.bit_arena.ptr, 0, bit_off[Lc + 1] * 4, st));
+  STB_CUDA(t, cudaMemsetAsync(sc.counts.ptr, 0, 80 * 4, st));
+  STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
+  {
+    BuildFlags init{~0ull, 0u, 0u};
+    STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    std::vector<uint32_t> sizes(Lc + 2, 0);
+    for (int j = 0; j <= Lc; ++j) sizes[j] = (uint32_t)n[j];
+    STB_CUDA(t, cudaMemcpyAsync(sc.level_sizes.ptr, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, st));
+    STB_CUDA(t, cudaStreamSynchronize(st));  // `sizes` and `init` are stack memory
+  }
+  STB_CUDA(t, t.leaves.alloc(std::min<uint64_t>(n0, direct_entries), st));
+  t.layers.clear();
+  for (int j = 1; j <= Lc; ++j) {
+    t.layers.emplace_back();
+    STB_CUDA(t, t.layers.back().nodes.alloc(n[j], st));
+  }
+  std::vector<uint32_t> serial(Lc + 1, 0);
+  for (int j = 1; j <= Lc; ++j) serial[j] = ++sc.serial;
+
+  // all chunk copies are queued at once on their own stream; compute waits chunk by chunk
+  if (!sc.copy_stream) STB_CUDA(t, cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
+  const uint64_t chunks = ceil_div(n0, C);
+  while (sc.chunk_events.size() < chunks) {
+    cudaEvent_t e;
+    STB_CUDA(t, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    sc.chunk_events.push_back(e);
+  }
+  char* text = t.staging.ptr;
+  for (uint64_t c = 0; c < chunks; ++c) {
+    const uint64_t first = c * C, cnt = std::min<uint64_t>(C, n0 - first);
+    STB_CUDA(t, cudaMemcpyAsync(text + first * S, h_body + first * S, cnt * S, cudaMemcpyHostToDevice, sc.copy_stream));
+    STB_CUDA(t, cudaEventRecord(sc.chunk_events[c], sc.copy_stream));
+  }
+
+  uint32_t* const ptrs = sc.ptr_arena.ptr;
+  uint32_t* const bits = sc.bit_arena.ptr;
+  uint32_t* const cnts = sc.cnt_arena.ptr;
+  LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
+  leaf_tab.first_bits = bits;
+  for (uint64_t c = 0; c < chunks; ++c) {
+    const uint64_t first = c * C, cnt = std::min<uint64_t>(C, n0 - first);
+    STB_CUDA(t, cudaStreamWaitEvent(st, sc.chunk_events[c], 0));
+    // leaf level of this chunk
+    if (S == 12) launch_leaf_text<12, true>(t, text + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
+    else launch_leaf_text<0, true>(t, text + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
+    for (int j = 0; j <= Lc; ++j) {
+      const uint64_t begin = first >> j, end = ceil_div(first + cnt, 1ull << j);
+      const uint32_t fb = (uint32_t)(begin / LVL_TILE), nbk = (uint32_t)ceil_div(end - begin, LVL_TILE);
+      uint32_t* lvl_ptr = ptrs + ptr_off[j];
+      uint32_t* lvl_bits = bits + bit_off[j];
+      uint32_t* lvl_cnt = cnts + cnt_off[j];
+      LevelTable tab = leaf_tab;
+      if (j > 0) {
+        tab = LevelTable{sc.stream_slots.ptr + slot_off[j], nullptr, nullptr, table_cap(n[j])};
+        tab.first_bits = lvl_bits;
+        Launch l(t, "node_insert");
+        // placement by child id above the first node layer; child ids are bounded by the child level's size
+        const uint32_t* child_unique = j > 1 ? sc.level_sizes.ptr + (j - 1) : nullptr;
+        node_insert_kernel<<<nbk, LVL_THREADS, 0, st>>>(ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], (uint32_t)end, tab, lvl_ptr, child_unique,
+                                                         serial[j], SingletonFilter{}, fb);
+      }
+      {
+        Launch l(t, "bitmask_blockcnt");
+        bitmask_blockcnt_kernel<<<(unsigned)ceil_div((uint64_t)nbk * 32, 256), 256, 0, st>>>(lvl_bits + (uint64_t)fb * (LVL_TILE / 32), nbk, lvl_cnt + fb);
+      }
+      {
+        Launch l(t, "scan_blocks");
+        scan_blocks_kernel<<<1, 1024, 0, st>>>(lvl_cnt + fb, nbk, sc.counts.ptr + j, sc.counts.ptr + j);
+      }
+      {
+        Launch l(t, "assign_ids");
+        if (j == 0)
+          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, lvl_cnt, t.leaves.ptr, S, nullptr, 0u, fb);
+        else
+          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, lvl_cnt, t.layers[j - 1].nodes.ptr, S,
+                                                                ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], fb);
+      }
+      {
+        Launch l(t, "resolve_ids");
+        if (j == 0) resolve_kernel<true><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)std::min<uint64_t>(n[0], first + cnt), tab, lvl_bits, fb);
+        else resolve_kernel<false><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, fb);
+      }
     }
   }
-  return STB_OK;
+  // the top of the tree: everything above the last chunked level, as in the one-shot build
+  const uint64_t n_top = n[Lc];
+  STB_CUDA(t, sc.ptr_a.ensure(n_top, st));
+  STB_CUDA(t, sc.ptr_b.ensure(ceil_div(n_top, 2), st));
+  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n_top, LVL_TILE) * (LVL_TILE / 32), st));
+  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n_top, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.filter.ensure(filter_words(ceil_div(n_top, 2)), st));
+  {
+    bool grew = false;
+    STB_CUDA(t, sc.slots.ensure((uint64_t)table_cap(ceil_div(n_top, 2)) + 1, st, &grew));
+    if (grew) sc.tags_cleared = false;
+  }
+  STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, ptrs + ptr_off[Lc], n_top * 4, cudaMemcpyDeviceToDevice, st));
+  int more = 0;
+  uint32_t* cur = nullptr;
+  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n_top, sc.counts.ptr + 1 + Lc, &more, &cur));
+  return finish_build(t, sc, n0, Lc + more, cur, true);
 }
 
 int build_dispatch(Tree& t, const LeafInput& in, uint64_t n0) {
@@ -901,6 +1071,10 @@ int build_from_body(Tree& t, const char* d_body, uint64_t body_len) {
   in.body = d_body;
   return build_dispatch(t, in, body_len / (uint64_t)t.S);
 }
+
+// Host text: overlap the copy with the build when the input is large enough; -1 = not applicable
+// (small input, dna_size > 12, or non-ACGT symbols), the caller copies and builds in one shot.
+int build_from_host_body(Tree& t, const char* h_body, uint64_t body_len) { return build_streaming(t, h_body, body_len); }
 
 int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n) {
   LeafInput in;

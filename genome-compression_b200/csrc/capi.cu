@@ -200,6 +200,10 @@ int stb_clone(const stb_tree* tree, stb_tree** out) {
 int stb_build_from_body(stb_tree* tree, const char* body, uint64_t len, int memory) {
   if (!tree || (!body && len) || !valid_memory(memory)) return STB_ERR_INVALID_ARG;
   STB_TRY(use_device(tree));
+  if (memory == STB_HOST) {  // large host inputs: build chunk by chunk behind the copy
+    const int s = build_from_host_body(*tree, body, len);
+    if (s != -1) return s;
+  }
   DevBuf<char> hold;
   const char* d = nullptr;
   STB_TRY(to_device(*tree, body, len, memory, hold, &d));

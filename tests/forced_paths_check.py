@@ -1,5 +1,7 @@
-"""Run in a subprocess with STB_FILTER_MIN=1, so that the singleton filter of the first node
-layer (normally only used from 4M positions up) handles inputs small enough for the oracle."""
+"""Run in a subprocess with environment overrides that force the large-input code paths onto
+inputs small enough for the oracle:
+  STB_FILTER_MIN=1                                  singleton filter of the first node layer
+  STB_STREAM_CHUNK_LOG2=12 STB_STREAM_MIN_CHUNKS=2  streaming (chunked) build from host memory"""
 import sys
 from pathlib import Path
 
@@ -24,12 +26,29 @@ def main():
         got.sort(); want.sort()
         assert got.serialize() == want.serialize(), (name, S)
         assert np.array_equal(got.decode(), leaves)
+        if S <= 12:  # bare body in HOST memory: the entry point that streams large inputs
+            host = stb.SharedTree(S).build_from_body(text)
+            want2 = oracle.build(leaves, S)
+            assert host.layer_counts() == want2.layer_counts(), (name, S, "host body")
+            assert host.serialize() == want2.serialize(), (name, S, "host body")
+            assert np.array_equal(host.decode(), leaves)
     n = 7_000_000
     buf = torch.empty(n, dtype=torch.uint8, device="cuda")
     stb.synth_genome(buf, n, seed=11, repeat_permille=500)
     leaves = oracle.fasta_to_leaves(buf.cpu().numpy().tobytes(), 12)
     got, want = stb.SharedTree(12).build_from_body(buf), oracle.build(leaves, 12)
     assert got.serialize() == want.serialize()
+    tree = stb.SharedTree(12)
+    for _ in range(2):  # twice on one handle: the workspace (tables, epoch tags) is reused
+        host = tree.build_from_body(buf.cpu().numpy().tobytes())
+        assert host.serialize() == want.serialize(), "host body, synthetic"
+    host.sort(); want.sort()
+    assert host.serialize() == want.serialize()
+    # an IUPAC symbol in the middle: the streaming path must fall back, not mis-build
+    text = bytearray(buf[:1_200_000].cpu().numpy().tobytes())
+    text[600_001] = ord("N")
+    lv = oracle.fasta_to_leaves(bytes(text), 12)
+    assert stb.SharedTree(12).build_from_body(bytes(text)).serialize() == oracle.build(lv, 12).serialize()
     rng = np.random.default_rng(5)
     codes = np.array([1, 2, 4, 8, 3, 12, 7, 14, 0, 9, 5, 11, 13, 10, 6, 15], dtype=np.uint64)
     nib = codes[rng.integers(0, 16, size=(40000, 12))]

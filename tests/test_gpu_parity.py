@@ -260,13 +260,16 @@ def test_large_properties(stb):
     assert hashlib.sha256(tree.serialize()).digest() == hashlib.sha256(stream).digest()
 
 
-def test_singleton_filter_forced_small():
-    """The first node layer's singleton filter, forced on for inputs the oracle can check
-    (tests/forced_paths_check.py)."""
+@pytest.mark.parametrize("env", [{"STB_FILTER_MIN": "1"},
+                                 {"STB_STREAM_CHUNK_LOG2": "12", "STB_STREAM_MIN_CHUNKS": "2"},
+                                 {"STB_STREAM_CHUNK_LOG2": "15", "STB_STREAM_MIN_CHUNKS": "2", "STB_FILTER_MIN": "1"}])
+def test_large_input_paths_forced_small(env):
+    """The singleton filter and the streaming host build, forced onto inputs the oracle can
+    check (tests/forced_paths_check.py)."""
     import os
     import subprocess
     import sys
     from conftest import ROOT
-    env = dict(os.environ, STB_FILTER_MIN="1")
-    res = subprocess.run([sys.executable, str(ROOT / "tests" / "forced_paths_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    res = subprocess.run([sys.executable, str(ROOT / "tests" / "forced_paths_check.py")], env=dict(os.environ, **env),
+                         capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "forced_paths_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
