@@ -170,22 +170,55 @@ partition_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint6
   }
 }
 
+// Owner side.  The same three ideas as the single-GPU level (build.cu): a singleton filter in
+// front of the table (cells are private to the owner, who sees every record of its keys), the
+// first-occurrence bitmap kept by XOR toggles during the insert, and answers that touch the
+// table only for the records that turned out NOT to be first occurrences.
+constexpr uint32_t OWNER_SINGLETON = 0xffffffffu;  // slot marker: certified singleton, never in the table
+
+__device__ __forceinline__ void owner_filter_cell(unsigned long long key, uint32_t log2_bits, uint32_t& word, uint32_t& bit) {
+  const uint32_t h = (uint32_t)mix64(key) >> (32 - log2_bits);
+  word = h >> 5;
+  bit = 1u << (h & 31);
+}
+
+__global__ void __launch_bounds__(256)
+owner_filter_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t* plane_a, uint32_t* plane_b, uint32_t log2_bits) {
+  for (uint32_t j = blockIdx.x * 1024 + threadIdx.x; j < min(n, (blockIdx.x + 1) * 1024u); j += 256) {
+    uint32_t word, bit;
+    owner_filter_cell(__ldg(keys + j), log2_bits, word, bit);
+    if (atomicOr(plane_a + word, bit) & bit) atomicOr(plane_b + word, bit);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 owner_insert_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ gpos, uint32_t n, Slot* tab,
-                    uint32_t cap, uint32_t* __restrict__ slot_of) {
-  const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= n) return;
-  slot_of[j] = table_insert<true>(tab, cap, __ldg(keys + j), __ldg(gpos + j));
+                    uint32_t cap, uint32_t* __restrict__ slot_of, uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ plane_b,
+                    uint32_t log2_bits) {
+  for (uint32_t j = blockIdx.x * 1024 + threadIdx.x; j < min(n, (blockIdx.x + 1) * 1024u); j += 256) {
+    const unsigned long long key = __ldg(keys + j);
+    const uint32_t pos = __ldg(gpos + j);
+    if (plane_b) {
+      uint32_t word, bit;
+      owner_filter_cell(key, log2_bits, word, bit);
+      if (!(__ldcg(plane_b + word) & bit)) {
+        atomicOr(bitmap + (pos >> 5), 1u << (pos & 31));
+        slot_of[j] = OWNER_SINGLETON;
+        continue;
+      }
+    }
+    slot_of[j] = table_insert<true>(tab, cap, key, pos, bitmap);
+  }
 }
 
 __global__ void __launch_bounds__(256)
 owner_answer_kernel(const uint32_t* __restrict__ gpos, uint32_t n, const Slot* tab, uint32_t* __restrict__ slot_then_answer,
-                    uint32_t* __restrict__ bitmap) {
-  const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= n) return;
-  const uint32_t q = __ldcg(&tab[slot_then_answer[j]].minpos);
-  slot_then_answer[j] = q;
-  if (q == __ldg(gpos + j)) atomicOr(bitmap + (q >> 5), 1u << (q & 31));
+                    const uint32_t* __restrict__ bitmap) {
+  for (uint32_t j = blockIdx.x * 1024 + threadIdx.x; j < min(n, (blockIdx.x + 1) * 1024u); j += 256) {
+    const uint32_t pos = __ldg(gpos + j);
+    const bool first = (__ldcg(bitmap + (pos >> 5)) >> (pos & 31)) & 1u;
+    slot_then_answer[j] = first ? pos : __ldcg(&tab[slot_then_answer[j]].minpos);
+  }
 }
 
 // per-CTA popcount of 1024 words
@@ -412,11 +445,27 @@ int stb_dist_owner(stb_tree* ctx, const uint64_t* keys_dev, const uint32_t* gpos
     Launch l(t, "table_clear", false);
     STB_CUDA(t, cudaMemsetAsync(table_dev, 0xff, ((uint64_t)cap + 1) * sizeof(Slot), st));
   }
-  const unsigned nb = (unsigned)ceil_div(n_records, 256);
+  // singleton filter: two bit planes of 2^k bits, k up to 28 (2 x 32 MiB: L2-resident)
+  uint32_t log2_bits = 0;
+  DevBuf<uint32_t> planes;
+  if (n_records >= (1u << 16)) {
+    log2_bits = 22;
+    while (log2_bits < 28 && (1ull << log2_bits) < 2 * n_records) ++log2_bits;
+    const uint64_t words = (1ull << log2_bits) / 32;
+    STB_CUDA(t, planes.alloc(2 * words, st));
+    STB_CUDA(t, cudaMemsetAsync(planes.ptr, 0, 2 * words * 4, st));
+  }
+  uint32_t* plane_a = planes.ptr;
+  uint32_t* plane_b = planes.ptr ? planes.ptr + (1ull << log2_bits) / 32 : nullptr;
+  const unsigned nb = (unsigned)ceil_div(n_records, 1024);
+  if (plane_b) {
+    Launch l(t, "dist_owner_filter");
+    owner_filter_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(keys_dev), (uint32_t)n_records, plane_a, plane_b, log2_bits);
+  }
   {
     Launch l(t, "dist_owner_insert");
     owner_insert_kernel<<<nb, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(keys_dev), gpos_dev, (uint32_t)n_records,
-                                            reinterpret_cast<Slot*>(table_dev), cap, answers_dev);
+                                            reinterpret_cast<Slot*>(table_dev), cap, answers_dev, bitmap_dev, plane_b, log2_bits);
   }
   {
     Launch l(t, "dist_owner_answer");

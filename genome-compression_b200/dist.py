@@ -39,7 +39,7 @@ class ShardPlan:
     """Which positions of which level a rank owns."""
     n_leaves: int
     world: int
-    cut: int = 1 << 22  # a level with at most this many positions is finished on rank 0 (cheaper than its collectives)
+    cut: int = 1 << 24  # a level with at most this many positions is finished on rank 0 (cheaper than its collectives)
     shard: int = field(init=False)
 
     def __post_init__(self):
@@ -131,7 +131,10 @@ class CudaStages:
                                                              self._p(pointers), C.c_void_p(leaves_out.data_ptr())))
 
     def upper_levels(self, pointers, n, leaf_pointers):
-        tree = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
+        # one handle for every build: its workspace (tables, pointer arrays) is reused
+        if getattr(self, "_upper", None) is None:
+            self._upper = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
+        tree = self._upper
         tree._check(self.pkg.lib.stb_dist_upper_levels(tree._h, self._p(pointers), n, int(leaf_pointers)))
         return tree
 
@@ -253,7 +256,7 @@ class ThreadComm:
 
 
 class DistBuilder:
-    def __init__(self, stages, comm=None, cut: int = 1 << 22):
+    def __init__(self, stages, comm=None, cut: int = 1 << 24):
         self.st = stages
         self.comm = comm or TorchComm()
         self.rank, self.world = self.comm.rank, self.comm.world
