@@ -97,6 +97,14 @@ def _load() -> C.CDLL:
         "stb_dist_leaf_direct_minpos": [vp, vp, u64, u64, vp, vp, P(i32)],
         "stb_dist_leaf_direct_finish": [vp, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp],
         "stb_assemble": [vp, vp, u64, u64, P(u64), P(vp), u32, u64],
+        "stb_dist_peer_alloc": [vp, u64, P(vp), vp],
+        "stb_dist_peer_open": [vp, vp, P(vp)],
+        "stb_dist_peer_close": [vp, vp],
+        "stb_dist_peer_free": [vp, vp],
+        "stb_dist_peer_scatter": [vp, i32, vp, u64, u64, i32, i32, P(vp), u64, vp],
+        "stb_dist_peer_owner": [vp, i32, i32, P(vp), u64, u64, vp, u64, vp, vp, u64, vp],
+        "stb_dist_peer_finish": [vp, i32, vp, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp],
+        "stb_dist_peer_put": [vp, vp, vp, u64],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -106,6 +114,12 @@ def _load() -> C.CDLL:
     lib.stb_status_string.restype = cp
     lib.stb_last_error.argtypes = [vp]
     lib.stb_last_error.restype = cp
+    lib.stb_dist_peer_arena_bytes.argtypes = [i32, u64]
+    lib.stb_dist_peer_arena_bytes.restype = u64
+    lib.stb_dist_peer_answers.argtypes = [vp, i32, u64]
+    lib.stb_dist_peer_answers.restype = vp
+    lib.stb_dist_peer_payload.argtypes = [vp, i32, u64]
+    lib.stb_dist_peer_payload.restype = vp
     lib.stb_kernel_launches.argtypes = []
     lib.stb_kernel_launches.restype = u64
     return lib

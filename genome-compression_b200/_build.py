@@ -29,7 +29,7 @@ def _sources():
 
 
 def _deps():
-    return list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "shared_tree_b200.h"]
+    return list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "shared_tree_b200.h", HERE.parent / "include" / "shared_tree_b200_dist.h"]
 
 
 def _stale(target: Path, inputs) -> bool:

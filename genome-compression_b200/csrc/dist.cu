@@ -7,48 +7,9 @@
 // bitmap that every rank evaluates locally.
 #include <algorithm>
 
-#include "tree.h"
+#include "dist.cuh"
 
 namespace stb {
-
-constexpr int DP_THREADS = 256;
-constexpr int DP_ITEMS = 4;
-constexpr int DP_TILE = DP_THREADS * DP_ITEMS;
-constexpr int DP_WARPS = DP_THREADS / 32;
-constexpr int MAX_WORLD = 16;
-
-// second, independent hash for the owner-local table (the first one picks the owner)
-__device__ __forceinline__ unsigned long long owner_local_key(unsigned long long key) { return key; }
-
-__device__ __forceinline__ uint32_t owner_of(unsigned long long key, int world) {
-  unsigned long long k = key * 0x9E3779B97F4A7C15ull;
-  k ^= k >> 29;
-  k *= 0xBF58476D1CE4E5B9ull;
-  return __umulhi((uint32_t)(k >> 32), (uint32_t)world);
-}
-
-// (key, flags) of local position i.  KIND 0: packed leaf; KIND 1: pair of child pointers.
-template <int KIND>
-__device__ __forceinline__ void produce(const void* items, uint64_t n_items, int S, uint64_t i, unsigned long long& key,
-                                        uint32_t& flags) {
-  if (KIND == 0) {
-    key = canonical_leaf(__ldg(reinterpret_cast<const unsigned long long*>(items) + i), S, flags);
-  } else {
-    const uint32_t* cur = reinterpret_cast<const uint32_t*>(items);
-    uint32_t l, r;
-    if (2 * i + 1 < n_items) {
-      const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + i);
-      l = pr.x;
-      r = pr.y;
-    } else {
-      l = cur[2 * i];
-      r = PTR_NULL;
-    }
-    uint32_t cl, cr;
-    canonical_node(l, r, cl, cr, flags);
-    key = ((unsigned long long)cl << 32) | cr;
-  }
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(DP_THREADS)
@@ -75,44 +36,6 @@ partition_hist_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t
   }
   __syncthreads();
   if (threadIdx.x < world) hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
-}
-
-// one CTA per owner: exclusive scan of its row + row total
-__global__ void __launch_bounds__(1024) rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ row_total) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nblocks; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nblocks ? row[i] : 0u;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t before = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - v;
-    if (i < nblocks) row[i] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = before + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) row_total[blockIdx.x] = carry_s;
 }
 
 template <int KIND>
@@ -174,14 +97,6 @@ partition_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint6
 // front of the table (cells are private to the owner, who sees every record of its keys), the
 // first-occurrence bitmap kept by XOR toggles during the insert, and answers that touch the
 // table only for the records that turned out NOT to be first occurrences.
-constexpr uint32_t OWNER_SINGLETON = 0xffffffffu;  // slot marker: certified singleton, never in the table
-
-__device__ __forceinline__ void owner_filter_cell(unsigned long long key, uint32_t log2_bits, uint32_t& word, uint32_t& bit) {
-  const uint32_t h = (uint32_t)mix64(key) >> (32 - log2_bits);
-  word = h >> 5;
-  bit = 1u << (h & 31);
-}
-
 __global__ void __launch_bounds__(256)
 owner_filter_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t* plane_a, uint32_t* plane_b, uint32_t log2_bits) {
   for (uint32_t j = blockIdx.x * 1024 + threadIdx.x; j < min(n, (blockIdx.x + 1) * 1024u); j += 256) {
@@ -307,12 +222,6 @@ word_prefix_kernel(const uint32_t* __restrict__ bitmap, uint64_t n_words, const 
   }
 }
 
-__device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
-                                            uint64_t n_bits, uint64_t total_word, uint64_t q) {
-  if (q >= n_bits) return word_prefix[total_word];
-  return __ldg(word_prefix + (q >> 5)) + __popc(__ldg(bitmap + (q >> 5)) & ((1u << (q & 31)) - 1u));
-}
-
 // Position order: first occurrences append their item and get their pointer.
 template <int KIND>
 __global__ void __launch_bounds__(256)
@@ -339,16 +248,23 @@ finish_first_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
   pointers[i] = finish_pointer(id, f);
 }
 
-// Send order: every later occurrence gets the id of its key's first position.
+// Send order: every later occurrence gets the id of its key's first position.  SPARSE: answers
+// exist only for later occurrences (peer exchange); a first occurrence shows in the bitmap.
+template <bool SPARSE>
 __global__ void __launch_bounds__(256)
 finish_rest_kernel(uint64_t n_pos, uint64_t gpos0, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
                    uint64_t n_bits, uint64_t n_words, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ answers,
                    uint32_t* __restrict__ pointers) {
   const uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= n_pos) return;
-  const uint32_t m = __ldg(meta + j), q = __ldg(answers + j);
+  const uint32_t m = __ldg(meta + j);
   const uint32_t pos = m & IDX_MASK;
-  if ((uint64_t)q == gpos0 + pos) return;  // a first occurrence, done in position order
+  if (SPARSE) {
+    const uint64_t g = gpos0 + pos;
+    if ((__ldg(bitmap + (g >> 5)) >> (g & 31)) & 1u) return;
+  }
+  const uint32_t q = __ldcg(answers + j);
+  if (!SPARSE && (uint64_t)q == gpos0 + pos) return;  // a first occurrence, done in position order
   pointers[pos] = finish_pointer(rank_of(bitmap, word_prefix, n_bits, n_words, q), m & ~IDX_MASK);
 }
 
@@ -498,10 +414,10 @@ int stb_dist_rank_index(stb_tree* ctx, const uint32_t* bitmap_dev, uint64_t n_wo
   return STB_OK;
 }
 
-int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
-                    const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
-                    const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
-                    uint32_t* base_count_dev) {
+static int finish_level(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                        const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                        const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                        uint32_t* base_count_dev, bool sparse) {
   if (!ctx || (kind != 0 && kind != 1) || !bitmap_dev || !word_prefix_dev || !base_count_dev) return STB_ERR_INVALID_ARG;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
   Tree& t = *ctx;
@@ -520,10 +436,27 @@ int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_i
   }
   if (n_pos) {
     Launch l(t, "dist_finish_rest");
-    finish_rest_kernel<<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
+    if (sparse) finish_rest_kernel<true><<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
+    else finish_rest_kernel<false><<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
   }
   STB_CUDA(t, cudaGetLastError());
   return STB_OK;
+}
+
+int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                    const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                    const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                    uint32_t* base_count_dev) {
+  return finish_level(ctx, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, meta_dev, answers_dev,
+                      pointers_dev, layer_slice_dev, base_count_dev, false);
+}
+
+int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                         const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                         const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                         uint32_t* base_count_dev) {
+  return finish_level(ctx, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, meta_dev, answers_dev,
+                      pointers_dev, layer_slice_dev, base_count_dev, true);
 }
 
 int stb_dist_leaf_direct_minpos(stb_tree* ctx, const char* body_dev, uint64_t n_local, uint64_t gpos0, uint32_t* table_dev,

@@ -131,12 +131,62 @@ class CudaStages:
                                                              self._p(pointers), C.c_void_p(leaves_out.data_ptr())))
 
     def upper_levels(self, pointers, n, leaf_pointers):
+        """pointers: a device tensor or a raw device address."""
         # one handle for every build: its workspace (tables, pointer arrays) is reused
         if getattr(self, "_upper", None) is None:
             self._upper = self.pkg.SharedTree(self.dna_size, device=self.device_index, stream=self.stream)
         tree = self._upper
-        tree._check(self.pkg.lib.stb_dist_upper_levels(tree._h, self._p(pointers), n, int(leaf_pointers)))
+        ptr = C.c_void_p(pointers) if isinstance(pointers, int) else self._p(pointers)
+        tree._check(self.pkg.lib.stb_dist_upper_levels(tree._h, ptr, n, int(leaf_pointers)))
         return tree
+
+    # -- peer exchange (records written straight into the owners' memory) ------------------
+    supports_peer = True
+
+    def peer_arena_bytes(self, world, region_cap):
+        return int(self.pkg.lib.stb_dist_peer_arena_bytes(world, region_cap))
+
+    def peer_alloc(self, nbytes):
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._check(self.pkg.lib.stb_dist_peer_alloc(self.ctx._h, nbytes, C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def peer_open(self, handle):
+        ptr, buf = C.c_void_p(), (C.c_ubyte * 64)(*handle)
+        self._check(self.pkg.lib.stb_dist_peer_open(self.ctx._h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr):
+        self._check(self.pkg.lib.stb_dist_peer_close(self.ctx._h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr):
+        self._check(self.pkg.lib.stb_dist_peer_free(self.ctx._h, C.c_void_p(ptr)))
+
+    @staticmethod
+    def _ptr_array(ptrs):
+        return (C.c_void_p * len(ptrs))(*ptrs)
+
+    def peer_scatter(self, kind, items, n_items, gpos0, world, rank, arenas, region_cap, meta):
+        self._check(self.pkg.lib.stb_dist_peer_scatter(self.ctx._h, kind, self._p(items), n_items, gpos0, world, rank,
+                                                       self._ptr_array(arenas), region_cap, self._p(meta)))
+
+    def peer_owner(self, world, rank, arenas, region_cap, expected, table, table_slots, slot_scratch, planes, bitmap):
+        self._check(self.pkg.lib.stb_dist_peer_owner(self.ctx._h, world, rank, self._ptr_array(arenas), region_cap, expected,
+                                                     self._p(table), table_slots, self._p(slot_scratch), self._p(planes),
+                                                     planes.numel() if planes is not None else 0, self._p(bitmap)))
+
+    def peer_finish(self, kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, arena, world, region_cap, pointers,
+                    slice_out, base_count):
+        answers = self.pkg.lib.stb_dist_peer_answers(C.c_void_p(arena), world, region_cap)
+        self._check(self.pkg.lib.stb_dist_peer_finish(self.ctx._h, kind, self._p(items), n_items, gpos0, self._p(bitmap),
+                                                      self._p(word_prefix), n_level, self._p(meta), C.c_void_p(answers),
+                                                      self._p(pointers), self._p(slice_out), self._p(base_count)))
+
+    def peer_payload(self, arena, world, region_cap):
+        return int(self.pkg.lib.stb_dist_peer_payload(C.c_void_p(arena), world, region_cap))
+
+    def peer_put(self, dst_ptr, src, nbytes):
+        self._check(self.pkg.lib.stb_dist_peer_put(self.ctx._h, C.c_void_p(dst_ptr), self._p(src), nbytes))
 
     def upper_layers(self, upper):
         """[(count, int32[count,2] device tensor)] of the top layers + root."""
@@ -200,6 +250,24 @@ class TorchComm:
         dist.all_gather_object(out, x, group=self.group)
         return out
 
+    # -- peer exchange plumbing ----------------------------------------------------------------
+    def map_arenas(self, stages, own_ptr, handle):
+        """Swap CUDA IPC handles and map every other rank's arena; returns the base pointers in
+        rank order (own pointer at [rank])."""
+        handles = self.all_gather_object(handle)
+        return [own_ptr if r == self.rank else stages.peer_open(handles[r]) for r in range(self.world)]
+
+    def unmap_arenas(self, stages, ptrs):
+        for r, p in enumerate(ptrs):
+            if r != self.rank:
+                stages.peer_close(p)
+
+    def stream_barrier(self, token):
+        """Every rank's earlier work on its stream (peer stores included) is complete and visible
+        once this returns control to the stream: a one-element all-reduce."""
+        if self.world > 1:
+            dist.all_reduce(token, op=dist.ReduceOp.SUM, group=self.group)
+
 
 class ThreadComm:
     """Virtual ranks as threads of ONE process sharing one GPU: the same exchanges done by
@@ -254,17 +322,82 @@ class ThreadComm:
     def all_gather_object(self, x):
         return self._exchange(x)
 
+    # virtual ranks live in one address space and on one stream: pointers are shared as they
+    # are, and a host barrier between enqueues orders the kernels
+    def map_arenas(self, stages, own_ptr, handle):
+        return self._exchange(own_ptr)
+
+    def unmap_arenas(self, stages, ptrs):
+        pass
+
+    def stream_barrier(self, token):
+        self.sh.barrier.wait()
+
+
+class PeerBuffers:
+    """Everything the peer exchange keeps between levels and builds on one rank: the arena that
+    the other ranks write into, the owner's table and scratch, the level bitmap and rank index."""
+
+    def __init__(self, stages, comm, region_cap: int, n_level: int):
+        st, world, dev = stages, comm.world, stages.device
+        self.st, self.comm, self.region_cap, self.n_level = st, comm, region_cap, n_level
+        self.own, handle = st.peer_alloc(st.peer_arena_bytes(world, region_cap))
+        self.arenas = comm.map_arenas(st, self.own, handle)
+        self.table_slots = max(1024, 2 * world * region_cap) + 1
+        self.table = torch.empty(self.table_slots * 2, dtype=torch.int64, device=dev)
+        self.slot_scratch = torch.empty(max(1, world * region_cap), dtype=torch.int32, device=dev)
+        self.planes = torch.empty(2 * (1 << 28) // 32, dtype=torch.int32, device=dev) if world * region_cap >= (1 << 16) else None
+        self.meta = torch.empty(max(1, region_cap), dtype=torch.int32, device=dev)
+        n_words = ceil_div(n_level, 32)
+        self.bitmap = torch.empty(n_words, dtype=torch.int32, device=dev)
+        self.word_prefix = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
+        self.scratch = torch.empty(ceil_div(n_words, 1024) + 1, dtype=torch.int32, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def fits(self, region_cap: int, n_level: int) -> bool:
+        return region_cap <= self.region_cap and n_level <= self.n_level
+
+    def close(self):
+        """Local: once this rank's stream has drained, every peer store into its arena has landed
+        (each one precedes a collective this rank took part in)."""
+        if self.own:
+            self.st.sync()
+            self.comm.unmap_arenas(self.st, self.arenas)
+            self.st.peer_free(self.own)
+            self.own = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
 
 class DistBuilder:
-    def __init__(self, stages, comm=None, cut: int = 1 << 24):
+    def __init__(self, stages, comm=None, cut: int | None = None, exchange: str | None = None):
+        """exchange: "peer" (records written into the owners' memory by the stage kernels; needs
+        peer-mapped device memory: GPUs of one node) or "collective" (all-to-all by the
+        communicator).  Default: STB_DIST_EXCHANGE, else "peer" where the stages offer it."""
         self.st = stages
         self.comm = comm or TorchComm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.device = stages.device
-        self.cut = cut
+        self.cut = cut if cut is not None else 1 << int(os.environ.get("STB_DIST_CUT_LOG2", "24"))
+        if exchange is None:
+            exchange = os.environ.get("STB_DIST_EXCHANGE") or ("peer" if getattr(stages, "supports_peer", False) else "collective")
+        assert exchange in ("peer", "collective"), exchange
+        self.exchange = exchange
+        self.peer = None
+        self._pending = []
         self.collectives = 0
         self.trace = bool(int(os.environ.get("STB_DIST_TRACE", "0")))
         self._t0 = time.perf_counter()
+
+    def close(self):
+        """Gives the peer-mapped exchange memory back (also happens when the builder is collected)."""
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
 
     # -- collectives ------------------------------------------------------------------
     def _all_to_all(self, send, send_counts, recv_counts):
@@ -338,6 +471,43 @@ class DistBuilder:
         base, count, total = [int(v) & 0xFFFFFFFF for v in torch.cat([base_count, total]).tolist()]
         return pointers, LayerSlice(base, count, slice_out[:count]), total
 
+    # -- one level, peer exchange: nothing comes back to the host ------------------------------
+    def _peer_buffers(self, region_cap, n_level):
+        if self.peer is None or not self.peer.fits(region_cap, n_level):
+            if self.peer is not None:
+                self.peer.close()
+            self.peer = PeerBuffers(self.st, self.comm, region_cap, n_level)
+        return self.peer
+
+    def _level_peer(self, kind, items, n_items, gpos0, n_level, region_cap):
+        """region_cap: the largest number of positions a rank holds at this level (same on all ranks)."""
+        st, world, dev = self.st, self.world, self.device
+        self._trace(f"-- level n={n_level} (peer)")
+        pb = self._peer_buffers(region_cap, n_level)
+        cap = pb.region_cap
+        n_pos = n_items if kind == LEAF else ceil_div(n_items, 2)
+        n_words = ceil_div(n_level, 32)
+        bitmap = pb.bitmap[:n_words]
+        bitmap.zero_()
+        st.peer_scatter(kind, items, n_items, gpos0, world, self.rank, pb.arenas, cap, pb.meta)
+        self._trace("scatter to owners")
+        self.collectives += 1
+        self.comm.stream_barrier(pb.token)
+        self._trace("barrier")
+        st.peer_owner(world, self.rank, pb.arenas, cap, ceil_div(n_level, world), pb.table, pb.table_slots, pb.slot_scratch, pb.planes, bitmap)
+        self._trace("owner")
+        self._all_reduce_sum(bitmap)  # first-occurrence bits are disjoint across owners: sum == or; also the second barrier
+        self._trace("all_reduce bitmap")
+        word_prefix = pb.word_prefix[:n_words + 1]
+        st.rank_index(bitmap, n_words, word_prefix, pb.scratch)
+        pointers = torch.empty(n_pos, dtype=torch.int32, device=dev)
+        slice_out = torch.empty(n_pos if kind == LEAF else (n_pos, 2), dtype=torch.int64 if kind == LEAF else torch.int32, device=dev)
+        counts = torch.zeros(3, dtype=torch.int32, device=dev)  # base, count, level total
+        st.peer_finish(kind, items, n_items, gpos0, bitmap, word_prefix, n_level, pb.meta, pb.own, world, cap, pointers, slice_out, counts)
+        counts[2:3].copy_(word_prefix[n_words:n_words + 1])
+        self._trace("rank index + finish")
+        return pointers, slice_out, counts
+
     def _leaf_level_direct(self, body, n_local, gpos0, n_level):
         """ACGT-only leaves, dna_size <= 12: replicated direct table + all-reduce(MIN) instead of
         the record exchange.  Returns None when some rank saw another symbol."""
@@ -365,38 +535,71 @@ class DistBuilder:
         total = int(word_prefix[n_words].item()) & 0xFFFFFFFF
         self._trace("leaf ids + resolve")
         # every rank holds the whole (small) leaf table; rank 0's copy is the one that is gathered
-        sl = LayerSlice(0, total, leaves_out[:total]) if self.rank == 0 else LayerSlice(total, 0, leaves_out[:0])
-        return pointers, sl, total
+        if self.rank == 0:
+            return pointers, leaves_out, (0, total, total)
+        return pointers, leaves_out[:0], (total, 0, total)
 
     # -- whole build ------------------------------------------------------------------
+    def _run_level(self, kind, items, n_items, gpos0, plan, level):
+        """-> (pointers, slice items, (base, count, level total) as ints or as a device tensor)."""
+        n_level = plan.level_total(level)
+        if self.exchange == "peer":
+            return self._level_peer(kind, items, n_items, gpos0, n_level, max(1, plan.shard >> level))
+        pointers, sl, total = self._level(kind, items, n_items, gpos0, n_level)
+        return pointers, sl.items, (sl.base, sl.count, total)
+
     def build_from_leaves(self, local_leaves, n_leaves_total: int, leaf_level=None) -> DistTree:
         """local_leaves: int64 device tensor with this rank's range of packed leaves
         (ShardPlan.level_range(rank, 0)).  leaf_level: an already finished leaf level."""
         plan = ShardPlan(n_leaves_total, self.world, self.cut)
         lo, hi = plan.level_range(self.rank, 0)
-        totals, layers = [], []
         if leaf_level is None:
             assert local_leaves.numel() == hi - lo, (local_leaves.numel(), lo, hi)
-            leaf_level = self._level(LEAF, local_leaves, hi - lo, lo, plan.level_total(0))
-        pointers, leaves, total = leaf_level
-        totals.append(total)
+            leaf_level = self._run_level(LEAF, local_leaves, hi - lo, lo, plan, 0)
+        pointers = leaf_level[0]
+        done = [leaf_level[1:]]
         n_sharded = plan.sharded_levels()
         for level in range(1, n_sharded):
             lo, hi = plan.level_range(self.rank, level)
             prev_lo, prev_hi = plan.level_range(self.rank, level - 1)
             assert hi - lo == ceil_div(prev_hi - prev_lo, 2)
-            pointers, sl, total = self._level(NODE, pointers, prev_hi - prev_lo, lo, plan.level_total(level))
-            layers.append(sl)
-            totals.append(total)
-        # gather the last sharded level's pointers on rank 0 and finish there
+            pointers, items, counts = self._run_level(NODE, pointers, prev_hi - prev_lo, lo, plan, level)
+            done.append((items, counts))
+        # the last sharded level's pointers go to rank 0, which finishes alone
         last = n_sharded - 1
         per_rank = [plan.level_range(r, last)[1] - plan.level_range(r, last)[0] for r in range(self.world)]
-        gathered = self._gather_rows(pointers, per_rank, dst=0)
+        self._trace("-- upper levels")
         upper, root = None, None
+        pb = self.peer if self.exchange == "peer" else None
+        if pb is not None and sum(per_rank) * 4 <= self.world * pb.region_cap * 8:
+            payload = self.st.peer_payload(pb.arenas[0], self.world, pb.region_cap)
+            self.st.peer_put(payload + 4 * sum(per_rank[:self.rank]), pointers, 4 * per_rank[self.rank])
+            self.collectives += 1
+            self.comm.stream_barrier(pb.token)
+            self._trace("pointers to rank 0")
+            if self.rank == 0:
+                upper = self.st.upper_levels(payload, sum(per_rank), leaf_pointers=(n_sharded == 1))
+            self.collectives += 1
+            self.comm.stream_barrier(pb.token)  # rank 0 has read its arena: free for the next build
+        else:
+            gathered = self._gather_rows(pointers, per_rank, dst=0)
+            self._trace("pointers to rank 0")
+            if self.rank == 0:
+                upper = self.st.upper_levels(gathered, gathered.shape[0], leaf_pointers=(n_sharded == 1))
         if self.rank == 0:
-            upper = self.st.upper_levels(gathered, gathered.shape[0], leaf_pointers=(n_sharded == 1))
             root = upper.root()
-        return DistTree(self.st.dna_size, n_leaves_total, leaves, layers, totals, upper, root)
+        self._trace("upper levels on rank 0")
+        # unique counts: one host read for the whole build
+        on_device = [c for _, c in done if torch.is_tensor(c)]
+        host = torch.stack(on_device).tolist() if on_device else []
+        slices, totals = [], []
+        for items, c in done:
+            base, count, total = [int(v) & 0xFFFFFFFF for v in (host.pop(0) if torch.is_tensor(c) else c)]
+            if total >= 1 << 29:
+                raise OverflowError("a layer outgrew the 29-bit pointer index (src/shared_tree.cpp:54-67)")
+            slices.append(LayerSlice(base, count, items[:count]))
+            totals.append(total)
+        return DistTree(self.st.dna_size, n_leaves_total, slices[0], slices[1:], totals, upper, root)
 
     def build_from_body(self, local_body, n_bases_total: int) -> DistTree:
         """local_body: uint8 device tensor holding the bases of this rank's leaf range."""

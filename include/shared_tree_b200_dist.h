@@ -95,6 +95,53 @@ int stb_dist_upper_levels(stb_tree* tree, const uint32_t* pointers_dev, uint64_t
 int stb_assemble(stb_tree* tree, const uint64_t* leaves_dev, uint64_t n_leaves, uint64_t n_layers,
                  const uint64_t* layer_counts, const void* const* layers_dev, uint32_t root, uint64_t width);
 
+/* ---- peer exchange: stages 1-4 with the record exchange fused into the kernels ---------------
+ *
+ * Every rank allocates one ARENA (stb_dist_peer_alloc: plain cudaMalloc + a 64-byte CUDA IPC
+ * handle), the ranks swap handles (any host channel; dist.py uses all_gather_object) and map each
+ * other's arenas (stb_dist_peer_open).  `arenas[world]` below are those mapped base pointers,
+ * arenas[rank] the rank's own.  region_cap = the largest number of positions any rank holds at
+ * the level (every rank must pass the same value; the arena must hold
+ * stb_dist_peer_arena_bytes(world, region_cap)).  Per level:
+ *
+ *   stb_dist_peer_scatter   stage 1 + 2: records are grouped by owner in shared memory and
+ *                           written straight into the owners' arenas (NVLink stores)
+ *   -- barrier A: any collective on the same stream (dist.py: 1-element all-reduce) --
+ *   stb_dist_peer_owner     stage 3 + 4a: dedup; LATER occurrences get their answer written into
+ *                           the source's arena; first occurrences are marked in the bitmap only
+ *   -- all-reduce(sum) of the bitmap: also barrier B --
+ *   stb_dist_rank_index, stb_dist_peer_finish (answers = stb_dist_peer_answers(own arena))
+ *
+ * Nothing is read back by the host inside a level.  */
+uint64_t stb_dist_peer_arena_bytes(int world, uint64_t region_cap);
+int stb_dist_peer_alloc(stb_tree* ctx, uint64_t bytes, void** ptr_out, unsigned char* handle_out /* [64] */);
+int stb_dist_peer_open(stb_tree* ctx, const unsigned char* handle /* [64] */, void** ptr_out);
+int stb_dist_peer_close(stb_tree* ctx, void* ptr);
+int stb_dist_peer_free(stb_tree* ctx, void* ptr);
+/* meta_dev[n_positions]: as in stb_dist_partition (send order). */
+int stb_dist_peer_scatter(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0, int world, int rank,
+                          void* const* arenas, uint64_t region_cap, uint32_t* meta_dev);
+/* expected_records: the rank's fair share (sizes grids and the singleton filter; any number of
+ * records up to world * region_cap is handled).  table_dev: table_slots * 16 bytes with
+ * table_slots >= 2 * world * region_cap + 1 (only 2 * records + 1 of them are touched);
+ * slot_scratch_dev: world * region_cap words; planes_dev (may be NULL): planes_words words for the
+ * singleton filter; bitmap_dev: caller-zeroed, ceil(n_level_positions / 32) words. */
+int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas, uint64_t region_cap, uint64_t expected_records,
+                        void* table_dev, uint64_t table_slots, uint32_t* slot_scratch_dev, uint32_t* planes_dev,
+                        uint64_t planes_words, uint32_t* bitmap_dev);
+/* stb_dist_finish for sparse answers (only later occurrences were answered). */
+int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                         const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                         const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                         uint32_t* base_count_dev);
+/* Where the answers to the rank's own records arrive inside its arena. */
+const void* stb_dist_peer_answers(void* arena, int world, uint64_t region_cap);
+/* A free area of the arena between levels (the record regions: world * region_cap * 8 bytes),
+ * and a stream-ordered copy into it (dst may be a peer's): used to collect the last sharded
+ * level's pointers on rank 0. */
+void* stb_dist_peer_payload(void* arena, int world, uint64_t region_cap);
+int stb_dist_peer_put(stb_tree* ctx, void* dst_dev, const void* src_dev, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,23 +32,37 @@ def main():
     body = torch.empty(max(16, (hi - lo) * S), dtype=torch.uint8, device="cuda")
     if hi > lo:
         pkg.synth_genome(body, n_bases, first=lo * S, count=(hi - lo) * S, seed=9, repeat_permille=500, device=local)
-    builder = DistBuilder(CudaStages(pkg, S, local))
-    tree = builder.build_from_body(body, n_bases)
-    full = builder.gather(tree)
+    single = single_pre = single_post = None
     if rank == 0:
         whole = torch.empty(n_bases, dtype=torch.uint8, device="cuda")
         pkg.synth_genome(whole, n_bases, seed=9, repeat_permille=500, device=local)
         single = pkg.SharedTree(S, device=local).build_from_body(whole)
-        assert full.layer_counts() == single.layer_counts(), (full.layer_counts(), single.layer_counts())
-        assert full.leaf_count() == single.leaf_count() and full.root() == single.root() and full.width() == single.width()
-        assert full.serialize() == single.serialize(), "pre-sort stream differs from the single-GPU build"
-        full.sort()
+        single_pre = single.serialize()
         single.sort()
-        assert full.serialize() == single.serialize(), "post-sort stream differs from the single-GPU build"
-        print(f"dist_gpu_check ok: world={world} bases={n_bases} leaves={full.leaf_count()} nodes={full.node_count()} "
-              f"collectives={builder.collectives}", flush=True)
+        single_post = single.serialize()
+        del whole
+    # several exchanged node levels (the default cut would leave only the leaf level sharded here);
+    # two builds per builder: the second one reuses the peer-mapped exchange memory
+    for exchange in ("peer", "collective"):
+        builder = DistBuilder(CudaStages(pkg, S, local), cut=1 << 12, exchange=exchange)
+        for _ in range(2):
+            tree = builder.build_from_body(body, n_bases)
+        full = builder.gather(tree)
+        if rank == 0:
+            check(world, n_bases, exchange, builder, full, single, single_pre, single_post)
+        builder.close()
     dist.barrier()
     dist.destroy_process_group()
+
+
+def check(world, n_bases, exchange, builder, full, single, single_pre, single_post):
+    assert full.layer_counts() == single.layer_counts(), (full.layer_counts(), single.layer_counts())
+    assert full.leaf_count() == single.leaf_count() and full.root() == single.root() and full.width() == single.width()
+    assert full.serialize() == single_pre, "pre-sort stream differs from the single-GPU build"
+    full.sort()
+    assert full.serialize() == single_post, "post-sort stream differs from the single-GPU build"
+    print(f"dist_gpu_check ok: world={world} exchange={exchange} bases={n_bases} leaves={full.leaf_count()} "
+          f"nodes={full.node_count()} collectives={builder.collectives}", flush=True)
 
 
 if __name__ == "__main__":

@@ -12,7 +12,10 @@ from conftest import ROOT, corpus_text
 pytestmark = pytest.mark.gpu
 
 
-def run_virtual(stb, world, leaves_np, S, cut):
+EXCHANGES = ("peer", "collective")
+
+
+def run_virtual(stb, world, leaves_np, S, cut, exchange="peer"):
     import torch
     from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan, ThreadComm
 
@@ -26,9 +29,10 @@ def run_virtual(stb, world, leaves_np, S, cut):
             torch.cuda.set_device(0)
             lo, hi = plan.level_range(rank, 0)
             local = torch.from_numpy(leaves_np[lo:hi].view(np.int64).copy()).cuda()
-            builder = DistBuilder(CudaStages(stb, S, 0), comm=ThreadComm(shared, rank), cut=cut)
+            builder = DistBuilder(CudaStages(stb, S, 0), comm=ThreadComm(shared, rank), cut=cut, exchange=exchange)
             tree = builder.build_from_leaves(local, n)
             results[rank] = builder.gather(tree)
+            builder.close()
         except Exception as e:  # noqa: BLE001
             errors.append(e)
             shared.barrier.abort()
@@ -41,11 +45,12 @@ def run_virtual(stb, world, leaves_np, S, cut):
     return results[0]
 
 
+@pytest.mark.parametrize("exchange", EXCHANGES)
 @pytest.mark.parametrize("world,cut", [(1, 1 << 16), (2, 64), (4, 1), (8, 1024)])
-def test_virtual_ranks_match_single_gpu(stb, oracle, world, cut):
+def test_virtual_ranks_match_single_gpu(stb, oracle, world, cut, exchange):
     text = corpus_text("merged")
     leaves = oracle.fasta_to_leaves(text, 12)
-    full = run_virtual(stb, world, leaves, 12, cut)
+    full = run_virtual(stb, world, leaves, 12, cut, exchange)
     single = stb.SharedTree(12).build_from_leaves(leaves)
     assert full.layer_counts() == single.layer_counts()
     assert full.serialize() == single.serialize() == oracle.build(leaves, 12).serialize()
@@ -66,9 +71,9 @@ def test_virtual_ranks_iupac_and_edges(stb, oracle, S, n):
         if S == 16:
             leaves[[3, 99, n - 1]] = np.uint64(0xFFFFFFFFFFFFFFFF)
     want = oracle.build(leaves, S)
-    for world in (2, 3):
-        full = run_virtual(stb, world, leaves, S, cut=16)
-        assert full.serialize() == want.serialize(), (S, n, world)
+    for world, exchange in ((2, "peer"), (3, "peer"), (3, "collective")):
+        full = run_virtual(stb, world, leaves, S, cut=16, exchange=exchange)
+        assert full.serialize() == want.serialize(), (S, n, world, exchange)
 
 
 def test_virtual_ranks_synthetic_large(stb):
@@ -78,9 +83,10 @@ def test_virtual_ranks_synthetic_large(stb):
     stb.synth_genome(buf, n_bases, seed=3, repeat_permille=500)
     single = stb.SharedTree(12).build_from_body(buf)
     leaves = stb.SharedTree(12).pack_fasta(buf)
-    full = run_virtual(stb, 4, leaves, 12, cut=1 << 14)
-    assert full.layer_counts() == single.layer_counts()
-    assert full.serialize() == single.serialize()
+    for exchange in EXCHANGES:
+        full = run_virtual(stb, 4, leaves, 12, cut=1 << 14, exchange=exchange)
+        assert full.layer_counts() == single.layer_counts()
+        assert full.serialize() == single.serialize()
 
 
 def test_nccl_two_ranks(stb):
@@ -113,6 +119,7 @@ def test_virtual_ranks_from_text_direct_leaf_table(stb, oracle):
                 body = torch.frombuffer(bytearray(text[lo * S:hi * S] + b"A" * 16), dtype=torch.uint8).cuda()
                 builder = DistBuilder(CudaStages(stb, S, 0), comm=ThreadComm(shared, rank), cut=64)
                 out[rank] = builder.gather(builder.build_from_body(body, n * S))
+                builder.close()
             except Exception as e:  # noqa: BLE001
                 errors.append(e)
                 shared.barrier.abort()
