@@ -352,8 +352,9 @@ def run_b200(args):
 
 def run_b200_dist(args, world, rank, local_rank):
     """N > 1: the sharded build (genome-compression_b200/dist.py).  Strong scaling: the same
-    3.1 Gbp sequence split over the ranks by leaf range; per level one hash-owner all-to-all
-    and one bitmap all-reduce over NVLink (NCCL)."""
+    3.1 Gbp sequence split over the ranks by leaf range; per level the stage kernels write the
+    (key, position) records straight into their hash owner's memory over NVLink and the owners
+    write the answers back; NCCL carries one 4-byte barrier and the bitmap all-reduce."""
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -449,16 +450,20 @@ def run_b200_dist(args, world, rank, local_rank):
                    for name, rec in prof.items()}
         # algorithmic bytes of rank 0's share of the two table kernels
         positions = sum(plan.level_range(0, lv)[1] - plan.level_range(0, lv)[0] for lv in range(plan.sharded_levels()))
-        dom = max((k for k in kernels if k.startswith("dist_")), key=lambda k: kernels[k]["ms_per_step"])
-        alg = {"dist_owner_insert": 12 * positions, "dist_owner_answer": 12 * positions, "dist_partition_hist": 8 * positions,
-               "dist_partition_scatter": 24 * positions, "dist_finish_first": 20 * positions, "dist_finish_rest": 12 * positions}.get(dom, 12 * positions)
+        node_positions = positions - (plan.level_range(0, 0)[1] - plan.level_range(0, 0)[0])  # the ACGT leaf level is not exchanged
+        dom = max((k for k in kernels if k.startswith(("dist_", "peer_"))), key=lambda k: kernels[k]["ms_per_step"])
+        # bytes per record of the stage's streams (key 8, position 4, slot / answer / meta 4, pointer pair 8)
+        alg = {"peer_owner_insert": 16, "peer_owner_answer": 12, "peer_owner_filter": 8, "peer_hist": 8, "peer_scatter": 24,
+               "dist_owner_insert": 16, "dist_owner_answer": 12, "dist_partition_hist": 8, "dist_partition_scatter": 24,
+               "dist_finish_first": 20, "dist_finish_rest": 12}.get(dom, 12) * node_positions
         ach = alg / (kernels[dom]["ms_per_step"] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": workload_config(args, {"sharding": f"{world} ranks x {plan.shard} leaf positions, hash-owner all-to-all + bitmap "
-                                                         f"all-reduce per level, {plan.sharded_levels()} sharded levels, rest on rank 0"}),
+            "config": workload_config(args, {"sharding": f"{world} ranks x {plan.shard} leaf positions; {builder.exchange} exchange by hash owner + "
+                                                         f"bitmap all-reduce per level; {plan.sharded_levels()} sharded levels, levels of <= "
+                                                         f"{plan.cut} positions on rank 0"}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
                          "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,

@@ -102,8 +102,8 @@ def _load() -> C.CDLL:
         "stb_dist_peer_close": [vp, vp],
         "stb_dist_peer_free": [vp, vp],
         "stb_dist_peer_scatter": [vp, i32, vp, u64, u64, i32, i32, P(vp), u64, vp],
-        "stb_dist_peer_owner": [vp, i32, i32, P(vp), u64, u64, vp, u64, vp, vp, u64, vp],
-        "stb_dist_peer_finish": [vp, i32, vp, u64, u64, vp, vp, u64, vp, vp, vp, vp, vp],
+        "stb_dist_peer_owner": [vp, i32, i32, P(vp), u64, u64, vp, u64, u32, vp, vp, u64, vp],
+        "stb_dist_peer_finish": [vp, i32, vp, u64, u64, vp, vp, u64, vp, vp, i32, u64, vp, vp, vp],
         "stb_dist_peer_put": [vp, vp, vp, u64],
     }
     for name, args in sig.items():
@@ -116,8 +116,6 @@ def _load() -> C.CDLL:
     lib.stb_last_error.restype = cp
     lib.stb_dist_peer_arena_bytes.argtypes = [i32, u64]
     lib.stb_dist_peer_arena_bytes.restype = u64
-    lib.stb_dist_peer_answers.argtypes = [vp, i32, u64]
-    lib.stb_dist_peer_answers.restype = vp
     lib.stb_dist_peer_payload.argtypes = [vp, i32, u64]
     lib.stb_dist_peer_payload.restype = vp
     lib.stb_kernel_launches.argtypes = []

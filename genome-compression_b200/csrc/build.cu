@@ -177,58 +177,6 @@ leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n
   insert_leaf<DIRECT>(v, S, p, tab, tmp + p, flags);
 }
 
-// 128-bit CAS with an arbitrary expected value; returns the previous contents.
-__device__ __forceinline__ void cas_slot(Slot* s, unsigned long long exp_lo, unsigned long long exp_hi, unsigned long long new_lo,
-                                         unsigned long long new_hi, unsigned long long& old_lo, unsigned long long& old_hi) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b128 cmp, val, old;\n\t"
-      "mov.b128 cmp, {%2, %3};\n\t"
-      "mov.b128 val, {%4, %5};\n\t"
-      "atom.global.cas.b128 old, [%6], cmp, val;\n\t"
-      "mov.b128 {%0, %1}, old;\n\t"
-      "}"
-      : "=l"(old_lo), "=l"(old_hi)
-      : "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi), "l"(s)
-      : "memory");
-}
-
-// Node-level insert into an epoch-tagged table: a slot whose last word is not `serial` is stale
-// (left by an earlier level), i.e. empty; it is claimed by a 128-bit CAS against exactly what was
-// read, writing key, min-position and tag at once.  Probing starts at `s`; after `limit` occupied
-// slots it restarts once at `s_alt`.  Keeps the first-occurrence bitmap current (toggle_bit).
-__device__ __forceinline__ uint32_t tagged_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos, uint32_t serial,
-                                                  uint32_t s, uint32_t s_alt, uint32_t limit, uint32_t* first_bits) {
-  const unsigned long long fresh_hi = ((unsigned long long)serial << 32) | pos;
-  uint32_t steps = 0;
-  for (;;) {
-    unsigned long long k, w;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(w) : "l"(tab + s));
-    if ((uint32_t)(w >> 32) != serial) {
-      unsigned long long ok, ow;
-      cas_slot(tab + s, k, w, key, fresh_hi, ok, ow);
-      if (ok == k && ow == w) {
-        toggle_bit(first_bits, pos);
-        return s;
-      }
-      k = ok;
-      w = ow;  // somebody else claimed it in this epoch
-    }
-    if (k == key) {
-      if ((uint32_t)w > pos) {
-        const uint32_t old = atomicMin(&tab[s].minpos, pos);
-        if (old > pos) {
-          toggle_bit(first_bits, pos);
-          toggle_bit(first_bits, old);
-        }
-      }
-      return s;
-    }
-    if (++steps == limit) s = s_alt;
-    else if (++s == cap) s = 0;
-  }
-}
-
 // Singleton filter for the first node layer (its keys are pairs of leaf ids: no locality to
 // exploit, so every table access is a random HBM line).  Two bit planes that fit in L2: plane A
 // = "some position hashed here", plane B = "at least two did".  A position whose B bit stays

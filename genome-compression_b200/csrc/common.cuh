@@ -259,6 +259,58 @@ __device__ __forceinline__ uint32_t table_insert(Slot* tab, uint32_t cap, unsign
                                                  uint32_t* first_bits = nullptr) {
   return table_insert_from<PROBE_FIRST>(tab, cap, key, pos, __umulhi(hash64(key), cap), first_bits);
 }
+
+// 128-bit CAS with an arbitrary expected value; returns the previous contents.
+__device__ __forceinline__ void cas_slot(Slot* s, unsigned long long exp_lo, unsigned long long exp_hi, unsigned long long new_lo,
+                                         unsigned long long new_hi, unsigned long long& old_lo, unsigned long long& old_hi) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b128 cmp, val, old;\n\t"
+      "mov.b128 cmp, {%2, %3};\n\t"
+      "mov.b128 val, {%4, %5};\n\t"
+      "atom.global.cas.b128 old, [%6], cmp, val;\n\t"
+      "mov.b128 {%0, %1}, old;\n\t"
+      "}"
+      : "=l"(old_lo), "=l"(old_hi)
+      : "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi), "l"(s)
+      : "memory");
+}
+
+// Node-level insert into an epoch-tagged table: a slot whose last word is not `serial` is stale
+// (left by an earlier level), i.e. empty; it is claimed by a 128-bit CAS against exactly what was
+// read, writing key, min-position and tag at once.  Probing starts at `s`; after `limit` occupied
+// slots it restarts once at `s_alt`.  Keeps the first-occurrence bitmap current (toggle_bit).
+__device__ __forceinline__ uint32_t tagged_insert(Slot* tab, uint32_t cap, unsigned long long key, uint32_t pos, uint32_t serial,
+                                                  uint32_t s, uint32_t s_alt, uint32_t limit, uint32_t* first_bits) {
+  const unsigned long long fresh_hi = ((unsigned long long)serial << 32) | pos;
+  uint32_t steps = 0;
+  for (;;) {
+    unsigned long long k, w;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(k), "=l"(w) : "l"(tab + s));
+    if ((uint32_t)(w >> 32) != serial) {
+      unsigned long long ok, ow;
+      cas_slot(tab + s, k, w, key, fresh_hi, ok, ow);
+      if (ok == k && ow == w) {
+        toggle_bit(first_bits, pos);
+        return s;
+      }
+      k = ok;
+      w = ow;  // somebody else claimed it in this epoch
+    }
+    if (k == key) {
+      if ((uint32_t)w > pos) {
+        const uint32_t old = atomicMin(&tab[s].minpos, pos);
+        if (old > pos) {
+          toggle_bit(first_bits, pos);
+          toggle_bit(first_bits, old);
+        }
+      }
+      return s;
+    }
+    if (++steps == limit) s = s_alt;
+    else if (++s == cap) s = 0;
+  }
+}
 #endif
 
 // ---- host context ------------------------------------------------------------------

@@ -222,49 +222,16 @@ word_prefix_kernel(const uint32_t* __restrict__ bitmap, uint64_t n_words, const 
   }
 }
 
-// Position order: first occurrences append their item and get their pointer.
-template <int KIND>
-__global__ void __launch_bounds__(256)
-finish_first_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n_pos, int S, uint64_t gpos0,
-                    const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, uint64_t n_bits,
-                    uint64_t n_words, uint32_t* __restrict__ pointers, void* __restrict__ slice,
-                    uint32_t* __restrict__ base_count) {
-  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  const uint32_t base = rank_of(bitmap, word_prefix, n_bits, n_words, gpos0);
-  if (i == 0) {
-    base_count[0] = base;
-    base_count[1] = rank_of(bitmap, word_prefix, n_bits, n_words, gpos0 + n_pos) - base;
-  }
-  if (i >= n_pos) return;
-  const uint64_t g = gpos0 + i;
-  const uint32_t word = __ldg(bitmap + (g >> 5));
-  if (!((word >> (g & 31)) & 1u)) return;
-  const uint32_t id = __ldg(word_prefix + (g >> 5)) + __popc(word & ((1u << (g & 31)) - 1u));
-  unsigned long long key;
-  uint32_t f;
-  produce<KIND>(items, n_items, S, i, key, f);
-  if (KIND == 0) reinterpret_cast<unsigned long long*>(slice)[id - base] = key;
-  else reinterpret_cast<uint2*>(slice)[id - base] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
-  pointers[i] = finish_pointer(id, f);
-}
-
-// Send order: every later occurrence gets the id of its key's first position.  SPARSE: answers
-// exist only for later occurrences (peer exchange); a first occurrence shows in the bitmap.
-template <bool SPARSE>
+// Send order: every later occurrence gets the id of its key's first position.
 __global__ void __launch_bounds__(256)
 finish_rest_kernel(uint64_t n_pos, uint64_t gpos0, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix,
                    uint64_t n_bits, uint64_t n_words, const uint32_t* __restrict__ meta, const uint32_t* __restrict__ answers,
                    uint32_t* __restrict__ pointers) {
   const uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= n_pos) return;
-  const uint32_t m = __ldg(meta + j);
+  const uint32_t m = __ldg(meta + j), q = __ldg(answers + j);
   const uint32_t pos = m & IDX_MASK;
-  if (SPARSE) {
-    const uint64_t g = gpos0 + pos;
-    if ((__ldg(bitmap + (g >> 5)) >> (g & 31)) & 1u) return;
-  }
-  const uint32_t q = __ldcg(answers + j);
-  if (!SPARSE && (uint64_t)q == gpos0 + pos) return;  // a first occurrence, done in position order
+  if ((uint64_t)q == gpos0 + pos) return;  // a first occurrence, done in position order
   pointers[pos] = finish_pointer(rank_of(bitmap, word_prefix, n_bits, n_words, q), m & ~IDX_MASK);
 }
 
@@ -414,49 +381,25 @@ int stb_dist_rank_index(stb_tree* ctx, const uint32_t* bitmap_dev, uint64_t n_wo
   return STB_OK;
 }
 
-static int finish_level(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
-                        const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
-                        const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
-                        uint32_t* base_count_dev, bool sparse) {
+int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
+                    const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
+                    const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
+                    uint32_t* base_count_dev) {
   if (!ctx || (kind != 0 && kind != 1) || !bitmap_dev || !word_prefix_dev || !base_count_dev) return STB_ERR_INVALID_ARG;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
   Tree& t = *ctx;
   cudaStream_t st = t.stream;
   const uint64_t n_pos = kind == 0 ? n_items : ceil_div(n_items, 2);
-  const uint64_t n_words = ceil_div(n_level_positions, 32);
-  const unsigned nb = (unsigned)std::max<uint64_t>(1, ceil_div(n_pos, 256));
-  {
-    Launch l(t, "dist_finish_first");
-    if (kind == 0)
-      finish_first_kernel<0><<<nb, 256, 0, st>>>(items_dev, n_items, n_pos, t.S, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
-                                                 pointers_dev, layer_slice_dev, base_count_dev);
-    else
-      finish_first_kernel<1><<<nb, 256, 0, st>>>(items_dev, n_items, n_pos, t.S, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
-                                                 pointers_dev, layer_slice_dev, base_count_dev);
-  }
+  STB_TRY(finish_first(t, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, pointers_dev, layer_slice_dev,
+                       base_count_dev));
   if (n_pos) {
+    const uint64_t n_words = ceil_div(n_level_positions, 32);
     Launch l(t, "dist_finish_rest");
-    if (sparse) finish_rest_kernel<true><<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
-    else finish_rest_kernel<false><<<nb, 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words, meta_dev, answers_dev, pointers_dev);
+    finish_rest_kernel<<<(unsigned)ceil_div(n_pos, 256), 256, 0, st>>>(n_pos, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
+                                                                       meta_dev, answers_dev, pointers_dev);
   }
   STB_CUDA(t, cudaGetLastError());
   return STB_OK;
-}
-
-int stb_dist_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
-                    const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
-                    const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
-                    uint32_t* base_count_dev) {
-  return finish_level(ctx, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, meta_dev, answers_dev,
-                      pointers_dev, layer_slice_dev, base_count_dev, false);
-}
-
-int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
-                         const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
-                         const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
-                         uint32_t* base_count_dev) {
-  return finish_level(ctx, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, meta_dev, answers_dev,
-                      pointers_dev, layer_slice_dev, base_count_dev, true);
 }
 
 int stb_dist_leaf_direct_minpos(stb_tree* ctx, const char* body_dev, uint64_t n_local, uint64_t gpos0, uint32_t* table_dev,

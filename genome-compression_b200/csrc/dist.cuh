@@ -93,4 +93,47 @@ __device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap,
   return __ldg(word_prefix + (q >> 5)) + __popc(__ldg(bitmap + (q >> 5)) & ((1u << (q & 31)) - 1u));
 }
 
+// Position order: first occurrences append their item and get their pointer.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+finish_first_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n_pos, int S, uint64_t gpos0,
+                    const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, uint64_t n_bits,
+                    uint64_t n_words, uint32_t* __restrict__ pointers, void* __restrict__ slice,
+                    uint32_t* __restrict__ base_count) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint32_t base = rank_of(bitmap, word_prefix, n_bits, n_words, gpos0);
+  if (i == 0) {
+    base_count[0] = base;
+    base_count[1] = rank_of(bitmap, word_prefix, n_bits, n_words, gpos0 + n_pos) - base;
+  }
+  if (i >= n_pos) return;
+  const uint64_t g = gpos0 + i;
+  const uint32_t word = __ldg(bitmap + (g >> 5));
+  if (!((word >> (g & 31)) & 1u)) return;
+  const uint32_t id = __ldg(word_prefix + (g >> 5)) + __popc(word & ((1u << (g & 31)) - 1u));
+  unsigned long long key;
+  uint32_t f;
+  produce<KIND>(items, n_items, S, i, key, f);
+  if (KIND == 0) reinterpret_cast<unsigned long long*>(slice)[id - base] = key;
+  else reinterpret_cast<uint2*>(slice)[id - base] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+  pointers[i] = finish_pointer(id, f);
+}
+
+// launches finish_first_kernel (shared by both exchanges)
+inline int finish_first(Tree& t, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0, const uint32_t* bitmap_dev,
+                        const uint32_t* word_prefix_dev, uint64_t n_level_positions, uint32_t* pointers_dev, void* layer_slice_dev,
+                        uint32_t* base_count_dev) {
+  const uint64_t n_pos = kind == 0 ? n_items : ceil_div(n_items, 2);
+  const uint64_t n_words = ceil_div(n_level_positions, 32);
+  const unsigned nb = (unsigned)(n_pos ? ceil_div(n_pos, 256) : 1);
+  Launch l(t, "dist_finish_first");
+  if (kind == 0)
+    finish_first_kernel<0><<<nb, 256, 0, t.stream>>>(items_dev, n_items, n_pos, t.S, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
+                                                     pointers_dev, layer_slice_dev, base_count_dev);
+  else
+    finish_first_kernel<1><<<nb, 256, 0, t.stream>>>(items_dev, n_items, n_pos, t.S, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, n_words,
+                                                     pointers_dev, layer_slice_dev, base_count_dev);
+  return STB_OK;
+}
+
 }  // namespace stb

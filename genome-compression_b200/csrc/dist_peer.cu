@@ -5,13 +5,14 @@
 // barrier).  Protocol in include/shared_tree_b200_dist.h ("peer exchange").
 //
 // Arena of one rank (identical layout on every rank, P = region capacity in records):
-//   hdr   [world]      {count, loc_off}: what source `src` sent me, and where that segment
-//                      starts in the source's own send order (for the answers)
-//   ans   [P]          answers to MY records, in my send order, written by their owners
-//   gpos  [world][P]   region `src`: global positions of the records source `src` sent me
-//   keys  [world][P]   region `src`: their keys
+//   hdr    [world]      count: how many records source `src` sent me
+//   cursor [world]      (private) how many records I have sent to owner o so far
+//   ans    [world][P]   region o: answers from owner o to MY records, in the order I sent them
+//   gpos   [world][P]   region `src`: global positions of the records source `src` sent me
+//   keys   [world][P]   region `src`: their keys
 // A region holds everything one source could ever send (all its positions), so no counts are
-// needed before writing and nothing can overflow.
+// needed before writing and nothing can overflow.  The order of the records inside a region is
+// whatever the CTAs' reservations made it; every result is independent of it.
 #include <algorithm>
 
 #include "dist.cuh"
@@ -19,7 +20,7 @@
 namespace stb {
 
 struct PeerHdr {
-  uint32_t count, loc_off, pad0, pad1;
+  uint32_t count, pad0, pad1, pad2;
 };
 
 struct PeerBases {
@@ -27,7 +28,7 @@ struct PeerBases {
 };
 
 struct ArenaLayout {
-  uint64_t hdr, ans, gpos, keys, bytes;
+  uint64_t hdr, cursor, ans, gpos, keys, bytes;
 };
 
 __host__ __device__ inline uint64_t up256(uint64_t x) { return (x + 255) & ~255ull; }
@@ -35,63 +36,32 @@ __host__ __device__ inline uint64_t up256(uint64_t x) { return (x + 255) & ~255u
 __host__ __device__ inline ArenaLayout arena_layout(int world, uint64_t P) {
   ArenaLayout L;
   L.hdr = 0;
-  L.ans = up256(MAX_WORLD * sizeof(PeerHdr));
-  L.gpos = L.ans + up256(P * 4);
+  L.cursor = up256(MAX_WORLD * sizeof(PeerHdr));  // MAX_WORLD cursors + the CTA completion count
+  L.ans = L.cursor + 256;
+  L.gpos = L.ans + up256((uint64_t)world * P * 4);
   L.keys = L.gpos + up256((uint64_t)world * P * 4);
   L.bytes = L.keys + up256((uint64_t)world * P * 8);
   return L;
 }
 
 // ---- source side: canonicalise, split by owner in shared memory, write the runs to the owners ----
-template <int KIND>
-__global__ void __launch_bounds__(DP_THREADS)
-peer_hist_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n_pos, int S, int world, uint32_t nblocks,
-                 uint32_t* __restrict__ hist) {
-  __shared__ uint32_t cnt[MAX_WORLD];
-  if (threadIdx.x < MAX_WORLD) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-  for (int it = 0; it < DP_ITEMS; ++it) {
-    const uint64_t i = (uint64_t)blockIdx.x * DP_TILE + it * DP_THREADS + threadIdx.x;
-    uint32_t o = 0xffffffffu;
-    if (i < n_pos) {
-      unsigned long long key;
-      uint32_t f;
-      produce<KIND>(items, n_items, S, i, key, f);
-      o = owner_of(key, world);
-    }
-    for (int w = 0; w < world; ++w) {
-      const uint32_t m = __ballot_sync(0xffffffffu, o == (uint32_t)w);
-      if (lane == 0 && m) atomicAdd(&cnt[w], (uint32_t)__popc(m));
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < world) hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
-}
-
+// One pass: a CTA reserves its run in every owner's region with one atomicAdd per owner on the
+// rank's cursors; the last CTA to finish publishes the final counts to the owners.
 template <int KIND>
 __global__ void __launch_bounds__(DP_THREADS)
 peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n_pos, int S, int world, int rank, uint64_t gpos0,
-                    uint32_t nblocks, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ row_total, PeerBases peers,
-                    uint64_t P, ArenaLayout L, uint32_t* __restrict__ meta) {
+                    PeerBases peers, uint64_t P, ArenaLayout L, uint32_t* __restrict__ meta) {
   __shared__ uint32_t cnt[DP_ITEMS * DP_WARPS][MAX_WORLD];  // per (row, warp) counts -> offsets inside the owner's run
   __shared__ uint32_t cta_off[MAX_WORLD + 1];               // owner's run inside this CTA's staged tile
   __shared__ uint32_t seg_off[MAX_WORLD];                   // where that run goes inside my region at the owner
-  __shared__ uint32_t loc_off[MAX_WORLD];                   // where the owner's segment starts in my send order
   __shared__ unsigned long long skey[DP_TILE];
   __shared__ uint32_t sgpos[DP_TILE], smeta[DP_TILE];
   __shared__ char* sbase[MAX_WORLD];
+  __shared__ bool last_cta;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int w = 0; w < MAX_WORLD; ++w)
     if (threadIdx.x == w) sbase[w] = peers.base[w];
-  if (threadIdx.x < MAX_WORLD) {
-    uint32_t b = 0;
-    for (int w = 0; w < (int)threadIdx.x && w < world; ++w) b += row_total[w];
-    loc_off[threadIdx.x] = b;
-    seg_off[threadIdx.x] = threadIdx.x < world ? hist[threadIdx.x * nblocks + blockIdx.x] : 0u;
-  }
   unsigned long long key[DP_ITEMS];
   uint32_t flg[DP_ITEMS], own[DP_ITEMS], rank_in_warp[DP_ITEMS];
 #pragma unroll
@@ -112,7 +82,8 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
     }
   }
   __syncthreads();
-  if (threadIdx.x < world) {  // exclusive scan over the (row, warp) sequence, per owner
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(sbase[rank] + L.cursor);
+  if (threadIdx.x < world) {  // exclusive scan over the (row, warp) sequence, per owner; then reserve the run
     uint32_t run = 0;
     for (int j = 0; j < DP_ITEMS * DP_WARPS; ++j) {
       const uint32_t c = cnt[j][threadIdx.x];
@@ -120,6 +91,7 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
       run += c;
     }
     cta_off[threadIdx.x + 1] = run;  // run length for now
+    seg_off[threadIdx.x] = run ? atomicAdd(cursor + threadIdx.x, run) : 0u;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -148,10 +120,18 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
     char* base = sbase[o];
     reinterpret_cast<unsigned long long*>(base + L.keys)[(uint64_t)rank * P + k] = skey[t];
     reinterpret_cast<uint32_t*>(base + L.gpos)[(uint64_t)rank * P + k] = sgpos[t];
-    meta[loc_off[o] + k] = smeta[t];
+    meta[(uint64_t)o * P + k] = smeta[t];
   }
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    PeerHdr h{row_total[threadIdx.x], loc_off[threadIdx.x], 0u, 0u};
+  // last CTA out publishes the counts (every reservation happened before its CTA's ticket)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last_cta = atomicAdd(cursor + MAX_WORLD, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last_cta && threadIdx.x < world) {
+    __threadfence();
+    PeerHdr h{__ldcg(cursor + threadIdx.x), 0u, 0u, 0u};
     reinterpret_cast<PeerHdr*>(sbase[threadIdx.x] + L.hdr)[rank] = h;
   }
 }
@@ -159,7 +139,6 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
 // ---- owner side: the records lie in `world` regions; one virtual index space over them ----
 struct OwnerView {
   uint32_t start[MAX_WORLD + 1];
-  uint32_t loc_off[MAX_WORLD];
 };
 
 __device__ __forceinline__ void load_view(OwnerView& v, const PeerHdr* __restrict__ hdr, int world) {
@@ -168,7 +147,6 @@ __device__ __forceinline__ void load_view(OwnerView& v, const PeerHdr* __restric
     for (int src = 0; src < world; ++src) {
       v.start[src] = run;
       run += __ldcg(&hdr[src].count);
-      v.loc_off[src] = __ldcg(&hdr[src].loc_off);
     }
     v.start[world] = run;
   }
@@ -181,14 +159,6 @@ __device__ __forceinline__ void locate(const OwnerView& v, int world, uint32_t j
   src = 0;
   while ((int)src + 1 < world && j >= v.start[src + 1]) ++src;
   k = j - v.start[src];
-}
-
-__global__ void __launch_bounds__(256) peer_table_clear_kernel(const PeerHdr* __restrict__ hdr, int world, uint4* __restrict__ tab) {
-  __shared__ OwnerView v;
-  load_view(v, hdr, world);
-  const uint64_t slots = (uint64_t)owner_cap(v.start[world]) + 1;
-  const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  for (uint64_t s = (uint64_t)blockIdx.x * 256 + threadIdx.x; s < slots; s += (uint64_t)gridDim.x * 256) tab[s] = ones;
 }
 
 __global__ void __launch_bounds__(256)
@@ -212,8 +182,9 @@ peer_owner_filter_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t
 }
 
 __global__ void __launch_bounds__(256)
-peer_owner_insert_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t P, int world, Slot* tab, uint32_t* __restrict__ slot_of,
-                         uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ plane_b, uint32_t log2_bits) {
+peer_owner_insert_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t P, int world, Slot* tab, uint32_t serial,
+                         uint32_t* __restrict__ slot_of, uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ plane_b,
+                         uint32_t log2_bits) {
   __shared__ OwnerView v;
   load_view(v, reinterpret_cast<const PeerHdr*>(arena + L.hdr), world);
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(arena + L.keys);
@@ -237,7 +208,7 @@ peer_owner_insert_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t
           continue;
         }
       }
-      slot_of[j] = table_insert<true>(tab, cap, key, pos, bitmap);
+      slot_of[j] = tagged_insert(tab, cap, key, pos, serial, __umulhi(hash64(key), cap), 0u, 0xffffffffu, bitmap);
     }
   }
 }
@@ -246,7 +217,7 @@ peer_owner_insert_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t
 // (the source recognises its own first occurrences from the all-reduced bitmap)
 __global__ void __launch_bounds__(256)
 peer_owner_answer_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t P, int world, const Slot* __restrict__ tab,
-                         const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ bitmap, PeerBases peers) {
+                         const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ bitmap, PeerBases peers, int rank) {
   __shared__ OwnerView v;
   __shared__ char* sbase[MAX_WORLD];
 #pragma unroll
@@ -264,7 +235,43 @@ peer_owner_answer_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t
       locate(v, world, (uint32_t)j, src, k);
       const uint32_t pos = __ldg(gpos + (uint64_t)src * P + k);
       if ((__ldcg(bitmap + (pos >> 5)) >> (pos & 31)) & 1u) continue;
-      reinterpret_cast<uint32_t*>(sbase[src] + L.ans)[v.loc_off[src] + k] = __ldcg(&tab[slot_of[j]].minpos);
+      reinterpret_cast<uint32_t*>(sbase[src] + L.ans)[(uint64_t)rank * P + k] = __ldcg(&tab[slot_of[j]].minpos);
+    }
+  }
+}
+
+// Back at the source, send order (regions by owner, cursor[o] records each): every later
+// occurrence gets the id of its key's first position; a first occurrence shows in the bitmap.
+__global__ void __launch_bounds__(256)
+peer_finish_rest_kernel(const char* __restrict__ arena, ArenaLayout L, uint64_t P, int world, uint64_t gpos0,
+                        const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ word_prefix, uint64_t n_bits, uint64_t n_words,
+                        const uint32_t* __restrict__ meta, uint32_t* __restrict__ pointers) {
+  __shared__ OwnerView v;
+  if (threadIdx.x == 0) {
+    const uint32_t* cursor = reinterpret_cast<const uint32_t*>(arena + L.cursor);
+    uint32_t run = 0;
+    for (int o = 0; o < world; ++o) {
+      v.start[o] = run;
+      run += __ldcg(cursor + o);
+    }
+    v.start[world] = run;
+  }
+  __syncthreads();
+  const uint32_t* ans = reinterpret_cast<const uint32_t*>(arena + L.ans);
+  const uint32_t m = v.start[world];
+  for (uint64_t tile = blockIdx.x; tile * 1024 < m; tile += gridDim.x) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const uint64_t j = tile * 1024 + it * 256 + threadIdx.x;
+      if (j >= m) break;
+      uint32_t o, k;
+      locate(v, world, (uint32_t)j, o, k);
+      const uint32_t mt = __ldg(meta + (uint64_t)o * P + k);
+      const uint32_t pos = mt & IDX_MASK;
+      const uint64_t g = gpos0 + pos;
+      if ((__ldg(bitmap + (g >> 5)) >> (g & 31)) & 1u) continue;
+      const uint32_t q = __ldcg(ans + (uint64_t)o * P + k);
+      pointers[pos] = finish_pointer(rank_of(bitmap, word_prefix, n_bits, n_words, q), mt & ~IDX_MASK);
     }
   }
 }
@@ -354,35 +361,23 @@ int stb_dist_peer_scatter(stb_tree* ctx, int kind, const void* items_dev, uint64
   STB_TRY(peer_bases(t, world, arenas, peers));
   const ArenaLayout L = arena_layout(world, region_cap);
   const uint32_t nblocks = (uint32_t)std::max<uint64_t>(1, ceil_div(n_pos, DP_TILE));
-  DevBuf<uint32_t> hist;
-  STB_CUDA(t, hist.alloc((uint64_t)world * nblocks + MAX_WORLD, st));
-  uint32_t* row_total = hist.ptr + (uint64_t)world * nblocks;
-  {
-    Launch l(t, "peer_hist");
-    if (kind == 0) peer_hist_kernel<0><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, nblocks, hist.ptr);
-    else peer_hist_kernel<1><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, nblocks, hist.ptr);
-  }
-  {
-    Launch l(t, "dist_rowscan");
-    rowscan_kernel<<<world, 1024, 0, st>>>(hist.ptr, nblocks, row_total);
-  }
+  STB_CUDA(t, cudaMemsetAsync(peers.base[rank] + L.cursor, 0, (MAX_WORLD + 1) * 4, st));
   {
     Launch l(t, "peer_scatter");
     if (kind == 0)
-      peer_scatter_kernel<0><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, rank, gpos0, nblocks, hist.ptr, row_total,
-                                                             peers, region_cap, L, meta_dev);
+      peer_scatter_kernel<0><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, rank, gpos0, peers, region_cap, L, meta_dev);
     else
-      peer_scatter_kernel<1><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, rank, gpos0, nblocks, hist.ptr, row_total,
-                                                             peers, region_cap, L, meta_dev);
+      peer_scatter_kernel<1><<<nblocks, DP_THREADS, 0, st>>>(items_dev, n_items, n_pos, t.S, world, rank, gpos0, peers, region_cap, L, meta_dev);
   }
   STB_CUDA(t, cudaGetLastError());
   return STB_OK;
 }
 
 int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas, uint64_t region_cap, uint64_t expected_records,
-                        void* table_dev, uint64_t table_slots, uint32_t* slot_scratch_dev, uint32_t* planes_dev,
+                        void* table_dev, uint64_t table_slots, uint32_t serial, uint32_t* slot_scratch_dev, uint32_t* planes_dev,
                         uint64_t planes_words, uint32_t* bitmap_dev) {
-  if (!ctx || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || !arenas || !table_dev || !slot_scratch_dev || !bitmap_dev)
+  if (!ctx || world < 1 || world > MAX_WORLD || rank < 0 || rank >= world || !arenas || !table_dev || !slot_scratch_dev || !bitmap_dev ||
+      serial == 0xffffffffu)
     return STB_ERR_INVALID_ARG;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
   Tree& t = *ctx;
@@ -398,11 +393,6 @@ int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas,
   // grids: sized for the expected share, grid-stride for whatever actually arrived
   const uint64_t expect = std::max<uint64_t>(expected_records, 1024);
   const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(expect, 1024) + 64, 1u << 20);
-  {
-    Launch l(t, "peer_table_clear");
-    const unsigned cb = (unsigned)std::min<uint64_t>(ceil_div(2 * expect + 1, 256 * 8), 148 * 16);
-    peer_table_clear_kernel<<<std::max(cb, 1u), 256, 0, st>>>(hdr, world, reinterpret_cast<uint4*>(table_dev));
-  }
   uint32_t log2_bits = 0;
   if (planes_dev && expected_records >= (1u << 16)) {
     log2_bits = 22;
@@ -422,21 +412,37 @@ int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas,
   }
   {
     Launch l(t, "peer_owner_insert");
-    peer_owner_insert_kernel<<<nb, 256, 0, st>>>(mine, L, region_cap, world, reinterpret_cast<Slot*>(table_dev), slot_scratch_dev, bitmap_dev,
-                                                 plane_b, log2_bits);
+    peer_owner_insert_kernel<<<nb, 256, 0, st>>>(mine, L, region_cap, world, reinterpret_cast<Slot*>(table_dev), serial, slot_scratch_dev,
+                                                 bitmap_dev, plane_b, log2_bits);
   }
   {
     Launch l(t, "peer_owner_answer");
     peer_owner_answer_kernel<<<nb, 256, 0, st>>>(mine, L, region_cap, world, reinterpret_cast<const Slot*>(table_dev), slot_scratch_dev, bitmap_dev,
-                                                 peers);
+                                                 peers, rank);
   }
   STB_CUDA(t, cudaGetLastError());
   return STB_OK;
 }
 
-const void* stb_dist_peer_answers(void* arena, int world, uint64_t region_cap) {
-  if (!arena || world < 1 || world > MAX_WORLD) return nullptr;
-  return static_cast<const char*>(arena) + arena_layout(world, region_cap).ans;
+int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0, const uint32_t* bitmap_dev,
+                         const uint32_t* word_prefix_dev, uint64_t n_level_positions, const uint32_t* meta_dev, const void* arena,
+                         int world, uint64_t region_cap, uint32_t* pointers_dev, void* layer_slice_dev, uint32_t* base_count_dev) {
+  if (!ctx || (kind != 0 && kind != 1) || !bitmap_dev || !word_prefix_dev || !base_count_dev || !arena || world < 1 || world > MAX_WORLD)
+    return STB_ERR_INVALID_ARG;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return STB_ERR_CUDA;
+  Tree& t = *ctx;
+  const uint64_t n_pos = kind == 0 ? n_items : ceil_div(n_items, 2);
+  STB_TRY(finish_first(t, kind, items_dev, n_items, gpos0, bitmap_dev, word_prefix_dev, n_level_positions, pointers_dev, layer_slice_dev,
+                       base_count_dev));
+  if (n_pos) {
+    Launch l(t, "peer_finish_rest");
+    peer_finish_rest_kernel<<<(unsigned)ceil_div(n_pos, 1024), 256, 0, t.stream>>>(static_cast<const char*>(arena), arena_layout(world, region_cap),
+                                                                                   region_cap, world, gpos0, bitmap_dev, word_prefix_dev,
+                                                                                   n_level_positions, ceil_div(n_level_positions, 32), meta_dev,
+                                                                                   pointers_dev);
+  }
+  STB_CUDA(t, cudaGetLastError());
+  return STB_OK;
 }
 
 void* stb_dist_peer_payload(void* arena, int world, uint64_t region_cap) {

@@ -34,15 +34,25 @@ def ceil_div(a: int, b: int) -> int:
     return -(-a // b)
 
 
+def default_cut(world: int) -> int:
+    """A level with at most this many positions is finished on rank 0: below it the per-level
+    collectives cost more than one GPU needs for the whole level.  Measured at 3.1 Gbp
+    (profiles/README.md): 2^24 is best on 2 GPUs, 2^22 on 8."""
+    env = os.environ.get("STB_DIST_CUT_LOG2")
+    return 1 << int(env) if env else max(1 << 20, (1 << 25) // max(1, world))
+
+
 @dataclass
 class ShardPlan:
     """Which positions of which level a rank owns."""
     n_leaves: int
     world: int
-    cut: int = 1 << 24  # a level with at most this many positions is finished on rank 0 (cheaper than its collectives)
+    cut: int | None = None  # see default_cut
     shard: int = field(init=False)
 
     def __post_init__(self):
+        if self.cut is None:
+            self.cut = default_cut(self.world)
         per = max(1, ceil_div(self.n_leaves, self.world))
         self.shard = 1 << (per - 1).bit_length()  # power of two >= per
 
@@ -170,16 +180,15 @@ class CudaStages:
         self._check(self.pkg.lib.stb_dist_peer_scatter(self.ctx._h, kind, self._p(items), n_items, gpos0, world, rank,
                                                        self._ptr_array(arenas), region_cap, self._p(meta)))
 
-    def peer_owner(self, world, rank, arenas, region_cap, expected, table, table_slots, slot_scratch, planes, bitmap):
+    def peer_owner(self, world, rank, arenas, region_cap, expected, table, table_slots, serial, slot_scratch, planes, bitmap):
         self._check(self.pkg.lib.stb_dist_peer_owner(self.ctx._h, world, rank, self._ptr_array(arenas), region_cap, expected,
-                                                     self._p(table), table_slots, self._p(slot_scratch), self._p(planes),
+                                                     self._p(table), table_slots, serial, self._p(slot_scratch), self._p(planes),
                                                      planes.numel() if planes is not None else 0, self._p(bitmap)))
 
     def peer_finish(self, kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, arena, world, region_cap, pointers,
                     slice_out, base_count):
-        answers = self.pkg.lib.stb_dist_peer_answers(C.c_void_p(arena), world, region_cap)
         self._check(self.pkg.lib.stb_dist_peer_finish(self.ctx._h, kind, self._p(items), n_items, gpos0, self._p(bitmap),
-                                                      self._p(word_prefix), n_level, self._p(meta), C.c_void_p(answers),
+                                                      self._p(word_prefix), n_level, self._p(meta), C.c_void_p(arena), world, region_cap,
                                                       self._p(pointers), self._p(slice_out), self._p(base_count)))
 
     def peer_payload(self, arena, world, region_cap):
@@ -344,10 +353,11 @@ class PeerBuffers:
         self.own, handle = st.peer_alloc(st.peer_arena_bytes(world, region_cap))
         self.arenas = comm.map_arenas(st, self.own, handle)
         self.table_slots = max(1024, 2 * world * region_cap) + 1
-        self.table = torch.empty(self.table_slots * 2, dtype=torch.int64, device=dev)
+        self.table = torch.full((self.table_slots * 2,), -1, dtype=torch.int64, device=dev)  # epoch-tagged: cleared once
+        self.serial = 0
         self.slot_scratch = torch.empty(max(1, world * region_cap), dtype=torch.int32, device=dev)
         self.planes = torch.empty(2 * (1 << 28) // 32, dtype=torch.int32, device=dev) if world * region_cap >= (1 << 16) else None
-        self.meta = torch.empty(max(1, region_cap), dtype=torch.int32, device=dev)
+        self.meta = torch.empty(max(1, world * region_cap), dtype=torch.int32, device=dev)
         n_words = ceil_div(n_level, 32)
         self.bitmap = torch.empty(n_words, dtype=torch.int32, device=dev)
         self.word_prefix = torch.empty(n_words + 1, dtype=torch.int32, device=dev)
@@ -382,7 +392,7 @@ class DistBuilder:
         self.comm = comm or TorchComm()
         self.rank, self.world = self.comm.rank, self.comm.world
         self.device = stages.device
-        self.cut = cut if cut is not None else 1 << int(os.environ.get("STB_DIST_CUT_LOG2", "24"))
+        self.cut = cut if cut is not None else default_cut(self.world)
         if exchange is None:
             exchange = os.environ.get("STB_DIST_EXCHANGE") or ("peer" if getattr(stages, "supports_peer", False) else "collective")
         assert exchange in ("peer", "collective"), exchange
@@ -494,7 +504,9 @@ class DistBuilder:
         self.collectives += 1
         self.comm.stream_barrier(pb.token)
         self._trace("barrier")
-        st.peer_owner(world, self.rank, pb.arenas, cap, ceil_div(n_level, world), pb.table, pb.table_slots, pb.slot_scratch, pb.planes, bitmap)
+        pb.serial += 1
+        st.peer_owner(world, self.rank, pb.arenas, cap, ceil_div(n_level, world), pb.table, pb.table_slots, pb.serial, pb.slot_scratch,
+                      pb.planes, bitmap)
         self._trace("owner")
         self._all_reduce_sum(bitmap)  # first-occurrence bits are disjoint across owners: sum == or; also the second barrier
         self._trace("all_reduce bitmap")

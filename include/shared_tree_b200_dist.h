@@ -110,7 +110,7 @@ int stb_assemble(stb_tree* tree, const uint64_t* leaves_dev, uint64_t n_leaves, 
  *   stb_dist_peer_owner     stage 3 + 4a: dedup; LATER occurrences get their answer written into
  *                           the source's arena; first occurrences are marked in the bitmap only
  *   -- all-reduce(sum) of the bitmap: also barrier B --
- *   stb_dist_rank_index, stb_dist_peer_finish (answers = stb_dist_peer_answers(own arena))
+ *   stb_dist_rank_index, stb_dist_peer_finish
  *
  * Nothing is read back by the host inside a level.  */
 uint64_t stb_dist_peer_arena_bytes(int world, uint64_t region_cap);
@@ -118,24 +118,26 @@ int stb_dist_peer_alloc(stb_tree* ctx, uint64_t bytes, void** ptr_out, unsigned 
 int stb_dist_peer_open(stb_tree* ctx, const unsigned char* handle /* [64] */, void** ptr_out);
 int stb_dist_peer_close(stb_tree* ctx, void* ptr);
 int stb_dist_peer_free(stb_tree* ctx, void* ptr);
-/* meta_dev[n_positions]: as in stb_dist_partition (send order). */
+/* meta_dev[world * region_cap]: local position | flags of every record sent, in send order
+ * (region o: the records that went to owner o). */
 int stb_dist_peer_scatter(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0, int world, int rank,
                           void* const* arenas, uint64_t region_cap, uint32_t* meta_dev);
 /* expected_records: the rank's fair share (sizes grids and the singleton filter; any number of
  * records up to world * region_cap is handled).  table_dev: table_slots * 16 bytes with
- * table_slots >= 2 * world * region_cap + 1 (only 2 * records + 1 of them are touched);
+ * table_slots >= 2 * world * region_cap + 1 (only 2 * records of them are touched), filled with
+ * 0xff bytes ONCE by the caller and never cleared again: slots carry an epoch tag, `serial` must
+ * be a value this table has not seen before (1, 2, 3, ...);
  * slot_scratch_dev: world * region_cap words; planes_dev (may be NULL): planes_words words for the
  * singleton filter; bitmap_dev: caller-zeroed, ceil(n_level_positions / 32) words. */
 int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas, uint64_t region_cap, uint64_t expected_records,
-                        void* table_dev, uint64_t table_slots, uint32_t* slot_scratch_dev, uint32_t* planes_dev,
+                        void* table_dev, uint64_t table_slots, uint32_t serial, uint32_t* slot_scratch_dev, uint32_t* planes_dev,
                         uint64_t planes_words, uint32_t* bitmap_dev);
-/* stb_dist_finish for sparse answers (only later occurrences were answered). */
+/* stb_dist_finish for the peer exchange: meta_dev as written by stb_dist_peer_scatter, the
+ * answers and the per-owner record counts are read from the rank's own arena. */
 int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_t n_items, uint64_t gpos0,
                          const uint32_t* bitmap_dev, const uint32_t* word_prefix_dev, uint64_t n_level_positions,
-                         const uint32_t* meta_dev, const uint32_t* answers_dev, uint32_t* pointers_dev, void* layer_slice_dev,
-                         uint32_t* base_count_dev);
-/* Where the answers to the rank's own records arrive inside its arena. */
-const void* stb_dist_peer_answers(void* arena, int world, uint64_t region_cap);
+                         const uint32_t* meta_dev, const void* arena, int world, uint64_t region_cap, uint32_t* pointers_dev,
+                         void* layer_slice_dev, uint32_t* base_count_dev);
 /* A free area of the arena between levels (the record regions: world * region_cap * 8 bytes),
  * and a stream-ordered copy into it (dst may be a peer's): used to collect the last sharded
  * level's pointers on rank 0. */
