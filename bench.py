@@ -304,7 +304,9 @@ def run_b200(args):
             return a.elapsed_time(b) / reps, out
 
         tree.build_from_body(text)
-        sort_ms, _ = timed(tree.sort)
+        sort_first_ms, _ = timed(tree.sort)   # first call: the stream-ordered pool grows by the sort's scratch
+        tree.build_from_body(text)
+        sort_ms, _ = timed(tree.sort)         # same work on the same unsorted tree, scratch served by the pool
         plan_ms, stream_bytes = timed(tree.bytes)
         dag = torch.empty(stream_bytes + 16, dtype=torch.uint8, device="cuda")
         ser_ms, _ = timed(lambda: tree.serialize_into(dag))
@@ -322,7 +324,7 @@ def run_b200(args):
         ra_ok = bool(torch.equal(got, leaves_out[idx]))
         del leaves_out, idx, got, dag
         pipeline = {
-            "sort_tree_ms": round(sort_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
+            "sort_tree_ms": round(sort_ms, 3), "sort_tree_first_call_ms": round(sort_first_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
             "stream_bytes": int(stream_bytes), "bits_per_base": round(8.0 * stream_bytes / bases_used, 4),
             "serialize_gbs": round(stream_bytes / (ser_ms * 1e-3) / 1e9, 1),
             "decode_ascii_ms": round(dec_ms, 3), "decode_ascii_gbp_s": round(bases_used / (dec_ms * 1e-3) / 1e9, 1),

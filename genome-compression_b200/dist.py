@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import time
 from dataclasses import dataclass, field
 
@@ -264,7 +265,21 @@ class TorchComm:
         """Swap CUDA IPC handles and map every other rank's arena; returns the base pointers in
         rank order (own pointer at [rank])."""
         handles = self.all_gather_object(handle)
-        return [own_ptr if r == self.rank else stages.peer_open(handles[r]) for r in range(self.world)]
+        if any(h is None for h in handles):
+            return None  # some rank could not allocate: everybody falls back together
+        ptrs, opened = [], []
+        try:
+            for r in range(self.world):
+                ptrs.append(own_ptr if r == self.rank else stages.peer_open(handles[r]))
+                if r != self.rank:
+                    opened.append(ptrs[-1])
+        except Exception:  # noqa: BLE001 - no peer access / IPC not permitted in this container
+            ptrs = None
+        if not all(self.all_gather_object(ptrs is not None)):
+            for p in opened:
+                stages.peer_close(p)
+            return None
+        return ptrs
 
     def unmap_arenas(self, stages, ptrs):
         for r, p in enumerate(ptrs):
@@ -334,13 +349,18 @@ class ThreadComm:
     # virtual ranks live in one address space and on one stream: pointers are shared as they
     # are, and a host barrier between enqueues orders the kernels
     def map_arenas(self, stages, own_ptr, handle):
-        return self._exchange(own_ptr)
+        ptrs = self._exchange(own_ptr if handle is not None else None)
+        return None if any(p is None for p in ptrs) else ptrs
 
     def unmap_arenas(self, stages, ptrs):
         pass
 
     def stream_barrier(self, token):
         self.sh.barrier.wait()
+
+
+class PeerUnavailable(RuntimeError):
+    """Peer-mapped exchange memory could not be set up on every rank."""
 
 
 class PeerBuffers:
@@ -350,8 +370,16 @@ class PeerBuffers:
     def __init__(self, stages, comm, region_cap: int, n_level: int):
         st, world, dev = stages, comm.world, stages.device
         self.st, self.comm, self.region_cap, self.n_level = st, comm, region_cap, n_level
-        self.own, handle = st.peer_alloc(st.peer_arena_bytes(world, region_cap))
+        try:
+            self.own, handle = st.peer_alloc(st.peer_arena_bytes(world, region_cap))
+        except Exception:  # noqa: BLE001
+            self.own, handle = 0, None
         self.arenas = comm.map_arenas(st, self.own, handle)
+        if self.arenas is None:
+            if self.own:
+                st.peer_free(self.own)
+                self.own = 0
+            raise PeerUnavailable("no peer-mapped exchange memory on this node; using the collective exchange")
         self.table_slots = max(1024, 2 * world * region_cap) + 1
         self.table = torch.full((self.table_slots * 2,), -1, dtype=torch.int64, device=dev)  # epoch-tagged: cleared once
         self.serial = 0
@@ -370,7 +398,7 @@ class PeerBuffers:
     def close(self):
         """Local: once this rank's stream has drained, every peer store into its arena has landed
         (each one precedes a collective this rank took part in)."""
-        if self.own:
+        if getattr(self, "own", 0):
             self.st.sync()
             self.comm.unmap_arenas(self.st, self.arenas)
             self.st.peer_free(self.own)
@@ -556,7 +584,12 @@ class DistBuilder:
         """-> (pointers, slice items, (base, count, level total) as ints or as a device tensor)."""
         n_level = plan.level_total(level)
         if self.exchange == "peer":
-            return self._level_peer(kind, items, n_items, gpos0, n_level, max(1, plan.shard >> level))
+            try:
+                return self._level_peer(kind, items, n_items, gpos0, n_level, max(1, plan.shard >> level))
+            except PeerUnavailable as e:  # raised on every rank together, before any stage ran
+                if self.rank == 0:
+                    print(f"[genome-compression_b200.dist] {e}", file=sys.stderr, flush=True)
+                self.exchange, self.peer = "collective", None
         pointers, sl, total = self._level(kind, items, n_items, gpos0, n_level)
         return pointers, sl.items, (sl.base, sl.count, total)
 

@@ -207,3 +207,127 @@ class NumpyStages:
 
     def sync(self):
         pass
+
+
+class _Arena:
+    """Numpy stand-in for one rank's peer-mapped exchange arena (csrc/dist_peer.cu)."""
+
+    def __init__(self, world, cap):
+        self.count = np.zeros(world, dtype=np.uint32)            # hdr: records received per source
+        self.cursor = np.zeros(world, dtype=np.uint32)           # records sent per owner
+        self.ans = np.zeros((world, cap), dtype=np.uint32)       # answers to my records, by owner
+        self.gpos = np.zeros((world, cap), dtype=np.uint32)      # received records, by source
+        self.keys = np.zeros((world, cap), dtype=np.uint64)
+        self.payload = np.zeros(world * cap * 2, dtype=np.uint32)
+
+
+class NumpyPeerStages(NumpyStages):
+    """Adds the peer-exchange stages: 'pointers' are indices into a process-wide arena list, so the
+    virtual ranks of ThreadComm (threads of this process) write into each other's arenas the way
+    the GPUs do over NVLink."""
+    supports_peer = True
+    _arenas: list = []
+    _lock = __import__("threading").Lock()
+
+    def peer_arena_bytes(self, world, region_cap):
+        return (world, region_cap)
+
+    def peer_alloc(self, shape):
+        with self._lock:
+            NumpyPeerStages._arenas.append(_Arena(*shape))
+            return len(NumpyPeerStages._arenas), b""  # 'address' 0 stays null
+
+    def peer_free(self, ptr):
+        NumpyPeerStages._arenas[ptr - 1] = None
+
+    def peer_scatter(self, kind, items, n_items, gpos0, world, rank, arenas, region_cap, meta):
+        recs = self._produce(kind, items, n_items)
+        assert len(recs) <= region_cap
+        mine = self._arenas[arenas[rank] - 1]
+        mine.cursor[:] = 0
+        m = _u32(meta).reshape(world, -1)
+        for i, (key, f) in reversed(list(enumerate(recs))):  # any order inside a region is legal
+            o = self._owner(key, world)
+            k = int(mine.cursor[o])
+            dst = self._arenas[arenas[o] - 1]
+            dst.keys[rank, k], dst.gpos[rank, k] = key, gpos0 + i
+            m[o, k] = i | f
+            mine.cursor[o] = k + 1
+        for o in range(world):
+            self._arenas[arenas[o] - 1].count[rank] = mine.cursor[o]
+
+    def peer_owner(self, world, rank, arenas, region_cap, expected, table, table_slots, serial, slot_scratch, planes, bitmap):
+        mine = self._arenas[arenas[rank] - 1]
+        first = {}
+        for src in range(world):
+            for k in range(int(mine.count[src])):
+                key, pos = int(mine.keys[src, k]), int(mine.gpos[src, k])
+                if key not in first or pos < first[key]:
+                    first[key] = pos
+        b = _u32(bitmap)
+        for src in range(world):
+            back = self._arenas[arenas[src] - 1].ans
+            for k in range(int(mine.count[src])):
+                key, pos = int(mine.keys[src, k]), int(mine.gpos[src, k])
+                q = first[key]
+                if q == pos:
+                    b[q >> 5] |= np.uint32(1 << (q & 31))
+                else:
+                    back[rank, k] = q  # sparse: only later occurrences are answered
+
+    def peer_finish(self, kind, items, n_items, gpos0, bitmap, word_prefix, n_level, meta, arena, world, region_cap, pointers,
+                    slice_out, base_count):
+        mine = self._arenas[arena - 1]
+        b, wp = _u32(bitmap), _u32(word_prefix)
+        n_words = (n_level + 31) // 32
+
+        def rank_of(q):
+            if q >= n_level:
+                return int(wp[n_words])
+            return int(wp[q >> 5]) + bin(int(b[q >> 5]) & ((1 << (q & 31)) - 1)).count("1")
+
+        recs = self._produce(kind, items, n_items)
+        base = rank_of(gpos0)
+        bc = _u32(base_count)
+        bc[0], bc[1] = base, rank_of(gpos0 + len(recs)) - base
+        ptr = _u32(pointers)
+        for i, (key, f) in enumerate(recs):
+            g = gpos0 + i
+            if (int(b[g >> 5]) >> (g & 31)) & 1:
+                ident = rank_of(g)
+                if kind == 0:
+                    slice_out.numpy().view(np.uint64)[ident - base] = key
+                else:
+                    s = _u32(slice_out)
+                    s[ident - base, 0], s[ident - base, 1] = key >> 32, key & 0xFFFFFFFF
+                ptr[i] = _finish(ident, f)
+        m = _u32(meta).reshape(world, -1)
+        for o in range(world):
+            for k in range(int(mine.cursor[o])):
+                pos = int(m[o, k]) & IDX
+                g = gpos0 + pos
+                if not (int(b[g >> 5]) >> (g & 31)) & 1:
+                    ptr[pos] = _finish(rank_of(int(mine.ans[o, k])), int(m[o, k]) & ~IDX & 0xFFFFFFFF)
+
+    def peer_payload(self, arena, world, region_cap):
+        return _PayloadRef(arena)
+
+    def peer_put(self, dst, src, nbytes):
+        n = nbytes // 4
+        self._arenas[dst.arena - 1].payload[dst.offset:dst.offset + n] = _u32(src)[:n]
+
+    def upper_levels(self, pointers, n, leaf_pointers):
+        if isinstance(pointers, _PayloadRef):
+            pointers = torch.from_numpy(self._arenas[pointers.arena - 1].payload[pointers.offset:pointers.offset + n].view(np.int32).copy())
+        return super().upper_levels(pointers, n, leaf_pointers)
+
+
+class _PayloadRef:
+    """payload 'address': arena + word offset; supports the `+ bytes` the builder does."""
+
+    def __init__(self, arena, offset=0):
+        self.arena, self.offset = arena, offset
+
+    def __add__(self, nbytes):
+        assert nbytes % 4 == 0
+        return _PayloadRef(self.arena, self.offset + nbytes // 4)

@@ -130,3 +130,92 @@ def test_thread_comm_virtual_ranks(oracle):
     assert np.array_equal(out[0].leaves_, want.leaves())
     assert all(np.array_equal(a, want.layer(k)) for k, a in enumerate(out[0].layers_))
     assert out[0].root_ == want.root()
+
+
+@pytest.mark.parametrize("world,n,S,cut,text", [(4, 700, 12, 8, False), (2, 333, 16, 1, False), (3, 515, 5, 4, True), (2, 1, 12, 1, True),
+                                                (3, 2, 12, 1, False)])
+def test_peer_exchange_orchestration_virtual_ranks(oracle, world, n, S, cut, text):
+    """The peer exchange's host logic (arenas, barriers, deferred counts, pointer hand-over to
+    rank 0, buffer reuse across builds) with numpy arenas shared by the virtual ranks."""
+    import threading
+    pkg = load_package()
+    sys.path.insert(0, str(ROOT / "tests"))
+    from dist_numpy_stages import NumpyPeerStages
+    from genome_compression_b200.dist import DistBuilder, ShardPlan, ThreadComm
+
+    leaves = make_leaves(n, S, 99 + n)
+    shared = ThreadComm.Shared(world)
+    plan = ShardPlan(n, world, cut)
+    out, errors, collectives = [None] * world, [], [0] * world
+
+    def work(rank):
+        try:
+            lo, hi = plan.level_range(rank, 0)
+            builder = DistBuilder(NumpyPeerStages(oracle, S), comm=ThreadComm(shared, rank), cut=cut)
+            assert builder.exchange == "peer"
+            for _ in range(2):  # the second build reuses arenas, table (new epoch) and cursors
+                if text:
+                    body = b"".join(pkg.leaf_to_str(v, S).encode() for v in leaves[lo:hi])
+                    tree = builder.build_from_body(torch.frombuffer(bytearray(body or b"A"), dtype=torch.uint8), n * S)
+                else:
+                    tree = builder.build_from_leaves(torch.from_numpy(leaves[lo:hi].view(np.int64).copy()), n)
+            out[rank] = (builder.gather(tree), tree.layer_totals)
+            collectives[rank] = builder.collectives
+            builder.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            shared.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    want = oracle.build(leaves, S)
+    full, totals = out[0]
+    assert np.array_equal(full.leaves_, want.leaves())
+    assert len(full.layers_) == want.depth() - 1
+    assert all(np.array_equal(a, want.layer(k)) for k, a in enumerate(full.layers_))
+    assert full.root_ == want.root()
+    assert totals[0] == want.leaf_count() and all(t == want.layer_count(k) for k, t in enumerate(totals[1:]))
+    assert len(set(collectives)) == 1  # every rank issued the same collectives
+
+
+def test_peer_exchange_falls_back_together(oracle):
+    """One rank cannot get peer-mapped memory: every rank switches to the collective exchange
+    before any stage ran, and the tree is the same."""
+    import threading
+    load_package()
+    sys.path.insert(0, str(ROOT / "tests"))
+    from dist_numpy_stages import NumpyPeerStages
+    from genome_compression_b200.dist import DistBuilder, ShardPlan, ThreadComm
+
+    class Broken(NumpyPeerStages):
+        def peer_alloc(self, shape):
+            raise MemoryError("no IPC here")
+
+    n, S, world, cut = 400, 12, 3, 4
+    leaves = make_leaves(n, S, 5)
+    shared = ThreadComm.Shared(world)
+    plan = ShardPlan(n, world, cut)
+    out, errors, modes = [None] * world, [], [None] * world
+
+    def work(rank):
+        try:
+            lo, hi = plan.level_range(rank, 0)
+            stages = (Broken if rank == 1 else NumpyPeerStages)(oracle, S)
+            builder = DistBuilder(stages, comm=ThreadComm(shared, rank), cut=cut)
+            out[rank] = builder.gather(builder.build_from_leaves(torch.from_numpy(leaves[lo:hi].view(np.int64).copy()), n))
+            modes[rank] = builder.exchange
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+            shared.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    assert modes == ["collective"] * world
+    want = oracle.build(leaves, S)
+    assert np.array_equal(out[0].leaves_, want.leaves())
+    assert all(np.array_equal(a, want.layer(k)) for k, a in enumerate(out[0].layers_))
+    assert out[0].root_ == want.root()
