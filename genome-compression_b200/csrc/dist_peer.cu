@@ -47,26 +47,31 @@ __host__ __device__ inline ArenaLayout arena_layout(int world, uint64_t P) {
 // ---- source side: canonicalise, split by owner in shared memory, write the runs to the owners ----
 // One pass: a CTA reserves its run in every owner's region with one atomicAdd per owner on the
 // rank's cursors; the last CTA to finish publishes the final counts to the owners.
+#ifndef PS_ITEMS
+#define PS_ITEMS 4
+#endif
+constexpr int PS_TILE = DP_THREADS * PS_ITEMS;  // records staged per CTA: runs of PS_TILE / world records per owner
+
 template <int KIND>
 __global__ void __launch_bounds__(DP_THREADS)
 peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n_pos, int S, int world, int rank, uint64_t gpos0,
                     PeerBases peers, uint64_t P, ArenaLayout L, uint32_t* __restrict__ meta) {
-  __shared__ uint32_t cnt[DP_ITEMS * DP_WARPS][MAX_WORLD];  // per (row, warp) counts -> offsets inside the owner's run
+  __shared__ uint32_t cnt[PS_ITEMS * DP_WARPS][MAX_WORLD];  // per (row, warp) counts -> offsets inside the owner's run
   __shared__ uint32_t cta_off[MAX_WORLD + 1];               // owner's run inside this CTA's staged tile
   __shared__ uint32_t seg_off[MAX_WORLD];                   // where that run goes inside my region at the owner
-  __shared__ unsigned long long skey[DP_TILE];
-  __shared__ uint32_t sgpos[DP_TILE], smeta[DP_TILE];
+  __shared__ unsigned long long skey[PS_TILE];
+  __shared__ uint32_t sgpos[PS_TILE], smeta[PS_TILE];
   __shared__ char* sbase[MAX_WORLD];
   __shared__ bool last_cta;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int w = 0; w < MAX_WORLD; ++w)
     if (threadIdx.x == w) sbase[w] = peers.base[w];
-  unsigned long long key[DP_ITEMS];
-  uint32_t flg[DP_ITEMS], own[DP_ITEMS], rank_in_warp[DP_ITEMS];
+  unsigned long long key[PS_ITEMS];
+  uint32_t flg[PS_ITEMS], own[PS_ITEMS], rank_in_warp[PS_ITEMS];
 #pragma unroll
-  for (int it = 0; it < DP_ITEMS; ++it) {
-    const uint64_t i = (uint64_t)blockIdx.x * DP_TILE + it * DP_THREADS + threadIdx.x;
+  for (int it = 0; it < PS_ITEMS; ++it) {
+    const uint64_t i = (uint64_t)blockIdx.x * PS_TILE + it * DP_THREADS + threadIdx.x;
     own[it] = 0xffffffffu;
     key[it] = 0;
     flg[it] = 0;
@@ -85,7 +90,7 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
   uint32_t* cursor = reinterpret_cast<uint32_t*>(sbase[rank] + L.cursor);
   if (threadIdx.x < world) {  // exclusive scan over the (row, warp) sequence, per owner; then reserve the run
     uint32_t run = 0;
-    for (int j = 0; j < DP_ITEMS * DP_WARPS; ++j) {
+    for (int j = 0; j < PS_ITEMS * DP_WARPS; ++j) {
       const uint32_t c = cnt[j][threadIdx.x];
       cnt[j][threadIdx.x] = run;
       run += c;
@@ -100,8 +105,8 @@ peer_scatter_kernel(const void* __restrict__ items, uint64_t n_items, uint64_t n
   }
   __syncthreads();
 #pragma unroll
-  for (int it = 0; it < DP_ITEMS; ++it) {
-    const uint64_t i = (uint64_t)blockIdx.x * DP_TILE + it * DP_THREADS + threadIdx.x;
+  for (int it = 0; it < PS_ITEMS; ++it) {
+    const uint64_t i = (uint64_t)blockIdx.x * PS_TILE + it * DP_THREADS + threadIdx.x;
     if (i < n_pos) {
       const uint32_t slot = cta_off[own[it]] + cnt[it * DP_WARPS + warp][own[it]] + rank_in_warp[it];
       skey[slot] = key[it];
@@ -360,7 +365,7 @@ int stb_dist_peer_scatter(stb_tree* ctx, int kind, const void* items_dev, uint64
   PeerBases peers;
   STB_TRY(peer_bases(t, world, arenas, peers));
   const ArenaLayout L = arena_layout(world, region_cap);
-  const uint32_t nblocks = (uint32_t)std::max<uint64_t>(1, ceil_div(n_pos, DP_TILE));
+  const uint32_t nblocks = (uint32_t)std::max<uint64_t>(1, ceil_div(n_pos, PS_TILE));
   STB_CUDA(t, cudaMemsetAsync(peers.base[rank] + L.cursor, 0, (MAX_WORLD + 1) * 4, st));
   {
     Launch l(t, "peer_scatter");
