@@ -64,17 +64,42 @@ def workload_config(args, extra=None):
 
 
 # ---------------------------------------------------------------------------- clocks
+def nvml_handle(index):
+    """NVML handle of CUDA device `index` of this process (matched by UUID: NVML's own numbering
+    ignores CUDA_VISIBLE_DEVICES)."""
+    import pynvml
+    import torch
+    pynvml.nvmlInit()
+    uuid = str(torch.cuda.get_device_properties(index).uuid)
+    if not uuid.startswith("GPU-"):
+        uuid = "GPU-" + uuid
+    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+
+
 class ClockSampler:
+    """SM clock and throttle reasons while the timed region runs: NVML polled every few
+    milliseconds from a thread (the timed region of a multi-GPU run lasts tens of milliseconds,
+    too short for an nvidia-smi loop); `nvidia-smi -lms` only when NVML cannot be loaded."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index=0):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index=0, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.proc = self.nvml = None
+        self.lines, self.sm, self.reason_bits = [], [], 0
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            self.nvml, self.handle = nvml_handle(self.index)
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -84,11 +109,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            n, bits = self.nvml, self.reason_bits
+            flags = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+                    "reasons": sorted(k for k, v in flags.items() if bits & v), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -98,7 +141,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
@@ -108,11 +150,27 @@ class ClockSampler:
                 mx.append(float(parts[2]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
+            for name, val in zip(self.NAMES, parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
+
+
+def bind_to_gpu_numa_node(index):
+    """One process per GPU: run (and first-touch pinned host buffers) on the cores NVML reports as
+    local to the GPU, so that the host-to-device copies of the e2e figure do not cross sockets."""
+    try:
+        pynvml, handle = nvml_handle(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------- reference arm / cpu baseline
@@ -303,15 +361,24 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps, out
 
+        def kernel_sum(fn):
+            tree.profile(True)
+            tree.profile_reset()
+            ms, out = timed(fn)
+            ksum = sum(r["ms"] for r in tree.profile_read().values())
+            tree.profile(False)
+            return ms, ksum, out
+
         tree.build_from_body(text)
         sort_first_ms, _ = timed(tree.sort)   # first call: the stream-ordered pool grows by the sort's scratch
         tree.build_from_body(text)
-        sort_ms, _ = timed(tree.sort)         # same work on the same unsorted tree, scratch served by the pool
+        sort_ms, sort_kernels_ms, _ = kernel_sum(tree.sort)  # same work on the same unsorted tree, scratch served by the pool
         plan_ms, stream_bytes = timed(tree.bytes)
         dag = torch.empty(stream_bytes + 16, dtype=torch.uint8, device="cuda")
         ser_ms, _ = timed(lambda: tree.serialize_into(dag))
         out = torch.empty(n0 * DNA, dtype=torch.uint8, device="cuda")
-        dec_ms, _ = timed(lambda: tree.decode_ascii(out=out))
+        dec_first_ms, _ = timed(lambda: tree.decode_ascii(out=out))
+        dec_ms, dec_kernels_ms, _ = kernel_sum(lambda: tree.decode_ascii(out=out))
         roundtrip_ok = bool(torch.equal(out, text[: n0 * DNA]))
         del out
         leaves_out = torch.empty(n0, dtype=torch.int64, device="cuda")
@@ -324,10 +391,12 @@ def run_b200(args):
         ra_ok = bool(torch.equal(got, leaves_out[idx]))
         del leaves_out, idx, got, dag
         pipeline = {
-            "sort_tree_ms": round(sort_ms, 3), "sort_tree_first_call_ms": round(sort_first_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
+            "sort_tree_ms": round(sort_ms, 3), "sort_tree_first_call_ms": round(sort_first_ms, 3),
+            "sort_tree_kernels_ms": round(sort_kernels_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
             "stream_bytes": int(stream_bytes), "bits_per_base": round(8.0 * stream_bytes / bases_used, 4),
             "serialize_gbs": round(stream_bytes / (ser_ms * 1e-3) / 1e9, 1),
-            "decode_ascii_ms": round(dec_ms, 3), "decode_ascii_gbp_s": round(bases_used / (dec_ms * 1e-3) / 1e9, 1),
+            "decode_ascii_ms": round(dec_ms, 3), "decode_ascii_first_call_ms": round(dec_first_ms, 3),
+            "decode_ascii_kernels_ms": round(dec_kernels_ms, 3), "decode_ascii_gbp_s": round(bases_used / (dec_ms * 1e-3) / 1e9, 1),
             "decode_leaves_ms": round(decl_ms, 3), "decode_roundtrip_equal": roundtrip_ok,
             "random_access_queries": q, "random_access_ms": round(ra_ms, 3),
             "random_access_mq_s": round(q / (ra_ms * 1e-3) / 1e6, 1), "random_access_equal": ra_ok,
@@ -380,6 +449,7 @@ def run_b200_dist(args, world, rank, local_rank):
         os.close(saved_stdout)
     pkg = load_package()
     from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan
+    local_cpus = bind_to_gpu_numa_node(local_rank)
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     peak_gbs, peak_src = 6650.0, "fallback"
@@ -444,8 +514,17 @@ def run_b200_dist(args, world, rank, local_rank):
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # for the record: the copies alone, all ranks at once (what PCIe and the host memory give)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            staging.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        ct = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
         e2e = {"value": bases_used / float(dt.item()) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": n_bases,
-               "d2h_bytes_per_step": 12 * len(tree.layer_totals) * world + 4, "ms_per_step": float(dt.item()) * 1e3, "steps": reps}
+               "d2h_bytes_per_step": 12 * len(tree.layer_totals) * world + 4, "ms_per_step": float(dt.item()) * 1e3, "steps": reps,
+               "h2d_copy_alone_ms": round(float(ct.item()) * 1e3, 3), "host_cores_bound_per_rank": local_cpus}
 
     if rank == 0:
         kernels = {name: {"ms_per_step": round(rec["ms"] / args.steps, 4), "launches_per_step": rec["launches"] // args.steps}

@@ -146,6 +146,7 @@ int stb_release_workspace(stb_tree* tree) {
   STB_TRY(use_device(tree));
   tree->workspace.reset();
   tree->staging.release();
+  tree->release_scratch();
   return STB_OK;
 }
 
@@ -155,6 +156,7 @@ int stb_destroy(stb_tree* tree) {
   tree->clear();
   tree->workspace.reset();
   tree->staging.release();
+  tree->release_scratch();
   cudaStreamSynchronize(tree->stream);
   delete tree;
   return STB_OK;

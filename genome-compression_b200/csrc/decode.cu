@@ -163,11 +163,10 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
   cudaStream_t st = t.stream;
   const int L = (int)t.layers.size();
   const uint64_t last = first + count - 1;
-  DevBuf<uint32_t> a, b;
-  STB_CUDA(t, a.alloc(count + 2, st));
-  STB_CUDA(t, b.alloc(count + 2, st));
-  uint32_t* cur = a.ptr;
-  uint32_t* nxt = b.ptr;
+  STB_CUDA(t, t.decode_a.ensure(count + 2, st));
+  STB_CUDA(t, t.decode_b.ensure(count + 2, st));
+  uint32_t* cur = t.decode_a.ptr;
+  uint32_t* nxt = t.decode_b.ptr;
   STB_CUDA(t, cudaMemcpyAsync(cur, &t.root, 4, cudaMemcpyHostToDevice, st));
   uint64_t lo_cur = 0;
   // pointer level k refers to node layer k and covers 2^(k+1) leaves; level -1 = leaf pointers

@@ -29,6 +29,13 @@ struct Tree : Ctx {
   // repeated builds on one handle do no device allocation.
   std::shared_ptr<void> workspace;
   DevBuf<char> staging;
+  // Scratch of decode (two ping-pong pointer arrays): grow-only as well, so repeated decodes on
+  // one handle allocate nothing.
+  DevBuf<uint32_t> decode_a, decode_b;
+  void release_scratch() {
+    decode_a.release();
+    decode_b.release();
+  }
 
   // serialization plan cache (per-layer byte totals), invalidated by build / sort
   bool plan_valid = false;
