@@ -56,6 +56,27 @@ leaves_out_kernel(const uint32_t* __restrict__ cur, unsigned long long n, const 
   out[j] = ptr_is_null(p) ? 0ull : apply_leaf(__ldg(leaves + (p & IDX_MASK)), p, S);
 }
 
+// from_nac (src/dna.cpp:51-74), "SACRGBNKTWVDYHM-" indexed by the 4-bit code, four codes at a
+// time: the table lives in four registers and PRMT is the lookup (a table in constant memory
+// would serialise on the divergent index).  q: four codes in bits 0..15 -> their four letters.
+__device__ __forceinline__ uint32_t nac_letters4(uint32_t q) {
+  const uint32_t sel = q & 0x7777u;
+  const uint32_t lo = __byte_perm(0x52434153u /* SACR */, 0x4b4e4247u /* GBNK */, sel);
+  const uint32_t hi = __byte_perm(0x44565754u /* TWVD */, 0x2d4d4859u /* YHM- */, sel);
+  return __byte_perm(lo, hi, 0x3210u + ((q & 0x8888u) >> 1));  // byte i from hi where code i has bit 3 set
+}
+
+// S letters of leaf v to (unaligned) shared memory
+__device__ __forceinline__ void spell_bytes(uint8_t* o, unsigned long long v, int S) {
+  for (int i = 0; i < S; i += 4) {
+    const uint32_t w = nac_letters4((uint32_t)(v >> (4 * i)) & 0xffffu);
+    o[i] = (uint8_t)w;
+    if (i + 1 < S) o[i + 1] = (uint8_t)(w >> 8);
+    if (i + 2 < S) o[i + 2] = (uint8_t)(w >> 16);
+    if (i + 3 < S) o[i + 3] = (uint8_t)(w >> 24);
+  }
+}
+
 constexpr int ASCII_TILE = 1024;
 __global__ void __launch_bounds__(DEC_THREADS)
 ascii_out_kernel(const uint32_t* __restrict__ cur, unsigned long long n, const unsigned long long* __restrict__ leaves,
@@ -65,16 +86,111 @@ ascii_out_kernel(const uint32_t* __restrict__ cur, unsigned long long n, const u
   const uint32_t here = (uint32_t)min((unsigned long long)ASCII_TILE, n - tile_first);
   const unsigned long long dst = tile_first * (unsigned long long)S;
   const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + dst) & 3ull);
-  // from_nac (src/dna.cpp:51-74), indexed by the 4-bit code
-  const char* letters = "SACRGBNKTWVDYHM-";
   for (uint32_t j = threadIdx.x; j < here; j += DEC_THREADS) {
     const uint32_t p = cur[tile_first + j];
     const unsigned long long v = ptr_is_null(p) ? 0ull : apply_leaf(__ldg(leaves + (p & IDX_MASK)), p, S);
-    uint8_t* o = stage + shift + j * S;
-    for (int i = 0; i < S; ++i) o[i] = (uint8_t)letters[(v >> (4 * i)) & 0xf];
+    spell_bytes(stage + shift + j * S, v, S);
   }
   __syncthreads();
   copy_out_staged<DEC_THREADS>(out + dst - shift, stage, shift, here * S);
+}
+
+// The last FUSE expansion steps and the output in one kernel: a thread takes one pointer into
+// node layer FUSE-1 (2^FUSE leaves), walks its subtree in registers (1 + 2 + 4 node reads) and
+// emits the leaves; the three largest intermediate pointer arrays (7/8 of the expansion's
+// traffic) are never written.  Used when the tree has at least FUSE node layers.
+constexpr int FUSE = 3;
+constexpr int FUSE_LEAVES = 1 << FUSE;
+
+__device__ __forceinline__ uint32_t child_of(uint2 nd, uint32_t parent, uint32_t side) {
+  const uint32_t m = (parent >> 29) & 1u, t = (parent >> 30) & 1u;
+  const uint32_t child = (side ^ m) ? nd.y : nd.x;  // mirrored parent: right first (:606-612)
+  return ptr_is_null(child) ? PTR_NULL : compose(child, m, t);
+}
+
+// Walks the 2^FUSE-leaf subtree under p2; calls emit(slot 0..7, leaf pointer) for every present leaf.
+// (Issuing all loads of a level before using any — nulls masked afterwards — was measured: slower.)
+template <class Emit>
+__device__ __forceinline__ void walk_subtree(uint32_t p2, const uint2* __restrict__ layer2, const uint2* __restrict__ layer1,
+                                             const uint2* __restrict__ layer0, Emit emit) {
+  if (ptr_is_null(p2)) return;
+  const uint2 nd2 = __ldg(layer2 + (p2 & IDX_MASK));
+#pragma unroll
+  for (uint32_t a = 0; a < 2; ++a) {
+    const uint32_t p1 = child_of(nd2, p2, a);
+    if (ptr_is_null(p1)) continue;
+    const uint2 nd1 = __ldg(layer1 + (p1 & IDX_MASK));
+#pragma unroll
+    for (uint32_t b = 0; b < 2; ++b) {
+      const uint32_t p0 = child_of(nd1, p1, b);
+      if (ptr_is_null(p0)) continue;
+      const uint2 nd0 = __ldg(layer0 + (p0 & IDX_MASK));
+#pragma unroll
+      for (uint32_t c = 0; c < 2; ++c) {
+        const uint32_t lp = child_of(nd0, p0, c);
+        if (!ptr_is_null(lp)) emit(4 * a + 2 * b + c, lp);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS)
+fused_leaves_kernel(const uint32_t* __restrict__ cur, unsigned long long lo_cur, const uint2* __restrict__ layer2,
+                    const uint2* __restrict__ layer1, const uint2* __restrict__ layer0, const unsigned long long* __restrict__ leaves,
+                    int S, unsigned long long first, unsigned long long count, unsigned long long* __restrict__ out) {
+  const unsigned long long last = first + count - 1;
+  const unsigned long long g = lo_cur + (unsigned long long)blockIdx.x * DEC_THREADS + threadIdx.x;
+  if (g * FUSE_LEAVES > last) return;
+  walk_subtree(cur[g - lo_cur], layer2, layer1, layer0, [&](uint32_t slot, uint32_t lp) {
+    const unsigned long long leaf = g * FUSE_LEAVES + slot;
+    if (leaf >= first && leaf <= last) out[leaf - first] = apply_leaf(__ldg(leaves + (lp & IDX_MASK)), lp, S);
+  });
+}
+
+// Text output in two phases so that both are free of bank conflicts: (1) thread t walks its
+// subtree and parks the 8 leaf values in shared memory, transposed (slot-major); (2) the
+// threads take consecutive leaves and spell them into the staged tile (word stores when the
+// leaf size and the destination allow it), which leaves the SM as aligned words.
+constexpr int FA_THREADS = 128;
+constexpr int FA_TILE = FA_THREADS * FUSE_LEAVES;  // 1024 leaves
+constexpr int FA_ROW = FA_THREADS + 2;             // slot-row stride: conflict-free reads by leaf order
+
+__global__ void __launch_bounds__(FA_THREADS)
+fused_ascii_kernel(const uint32_t* __restrict__ cur, unsigned long long lo_cur, const uint2* __restrict__ layer2,
+                   const uint2* __restrict__ layer1, const uint2* __restrict__ layer0, const unsigned long long* __restrict__ leaves,
+                   int S, unsigned long long first, unsigned long long count, char* __restrict__ out) {
+  __shared__ unsigned long long vals[FUSE_LEAVES * FA_ROW];
+  __shared__ __align__(16) uint8_t stage[FA_TILE * 16 + 16];
+  const unsigned long long last = first + count - 1;
+  const unsigned long long group0 = lo_cur + (unsigned long long)blockIdx.x * FA_THREADS;
+  const unsigned long long tile_base = group0 * FUSE_LEAVES;
+  const unsigned long long tile_lo = max(first, tile_base);
+  const unsigned long long tile_hi = min(last + 1, tile_base + FA_TILE);  // > tile_lo for every launched CTA
+  const unsigned long long dst = (tile_lo - first) * (unsigned long long)S;
+  const uint32_t shift = (uint32_t)((reinterpret_cast<uintptr_t>(out) + dst) & 3ull);
+  const unsigned long long g = group0 + threadIdx.x;
+  if (g * FUSE_LEAVES <= last)
+    walk_subtree(cur[g - lo_cur], layer2, layer1, layer0, [&](uint32_t slot, uint32_t lp) {
+      vals[slot * FA_ROW + threadIdx.x] = apply_leaf(__ldg(leaves + (lp & IDX_MASK)), lp, S);
+    });
+  __syncthreads();
+  const bool by_words = shift == 0 && (S & 3) == 0;
+#pragma unroll
+  for (int r = 0; r < FUSE_LEAVES; ++r) {
+    const uint32_t l = r * FA_THREADS + threadIdx.x;  // leaf inside the tile
+    const unsigned long long leaf = tile_base + l;
+    if (leaf < tile_lo || leaf >= tile_hi) continue;
+    const unsigned long long v = vals[(l & (FUSE_LEAVES - 1)) * FA_ROW + (l >> FUSE)];
+    const uint32_t at = shift + (uint32_t)(leaf - tile_lo) * S;
+    if (by_words) {
+      uint32_t* o = reinterpret_cast<uint32_t*>(stage + at);
+      for (int w = 0; w < S / 4; ++w) o[w] = nac_letters4((uint32_t)(v >> (16 * w)) & 0xffffu);
+    } else {
+      spell_bytes(stage + at, v, S);
+    }
+  }
+  __syncthreads();
+  copy_out_staged<FA_THREADS>(out + dst - shift, stage, shift, (uint32_t)(tile_hi - tile_lo) * S);
 }
 
 // operator[] batched: one thread per query, depth dependent gathers.
@@ -170,7 +286,8 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
   STB_CUDA(t, cudaMemcpyAsync(cur, &t.root, 4, cudaMemcpyHostToDevice, st));
   uint64_t lo_cur = 0;
   // pointer level k refers to node layer k and covers 2^(k+1) leaves; level -1 = leaf pointers
-  for (int k = L - 1; k >= 0; --k) {
+  const int stop = L >= FUSE ? FUSE : 0;  // pointer levels below `stop` are walked inside the output kernel
+  for (int k = L - 1; k >= stop; --k) {
     const uint64_t lo_next = first >> k, hi_next = last >> k;
     const uint64_t n_next = hi_next - lo_next + 1;
     {
@@ -180,13 +297,26 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
     std::swap(cur, nxt);
     lo_cur = lo_next;
   }
-  if (d_out) {
-    Launch l(t, "leaves_out");
-    leaves_out_kernel<<<(unsigned)ceil_div(count, DEC_THREADS), DEC_THREADS, 0, st>>>(cur, count, t.leaves.ptr, t.S, d_out);
-  }
-  if (d_ascii) {
-    Launch l(t, "ascii_out");
-    ascii_out_kernel<<<(unsigned)ceil_div(count, ASCII_TILE), DEC_THREADS, 0, st>>>(cur, count, t.leaves.ptr, t.S, d_ascii);
+  if (stop) {
+    const uint64_t groups = (last >> FUSE) - (first >> FUSE) + 1;
+    const uint2 *l2 = t.layers[2].nodes.ptr, *l1 = t.layers[1].nodes.ptr, *l0 = t.layers[0].nodes.ptr;
+    if (d_out) {
+      Launch l(t, "leaves_out_fused");
+      fused_leaves_kernel<<<(unsigned)ceil_div(groups, DEC_THREADS), DEC_THREADS, 0, st>>>(cur, lo_cur, l2, l1, l0, t.leaves.ptr, t.S, first, count, d_out);
+    }
+    if (d_ascii) {
+      Launch l(t, "ascii_out_fused");
+      fused_ascii_kernel<<<(unsigned)ceil_div(groups, FA_THREADS), FA_THREADS, 0, st>>>(cur, lo_cur, l2, l1, l0, t.leaves.ptr, t.S, first, count, d_ascii);
+    }
+  } else {
+    if (d_out) {
+      Launch l(t, "leaves_out");
+      leaves_out_kernel<<<(unsigned)ceil_div(count, DEC_THREADS), DEC_THREADS, 0, st>>>(cur, count, t.leaves.ptr, t.S, d_out);
+    }
+    if (d_ascii) {
+      Launch l(t, "ascii_out");
+      ascii_out_kernel<<<(unsigned)ceil_div(count, ASCII_TILE), DEC_THREADS, 0, st>>>(cur, count, t.leaves.ptr, t.S, d_ascii);
+    }
   }
   STB_CUDA(t, cudaStreamSynchronize(st));  // t.root was copied from host memory above
   STB_CUDA(t, cudaGetLastError());

@@ -223,15 +223,21 @@ __global__ void widen_kernel(const uint32_t* __restrict__ in, uint32_t n, unsign
 
 static uint64_t child_count(const Tree& t, uint64_t layer) { return layer == 0 ? t.n_leaves : t.layers[layer - 1].count; }
 
-int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq) {
+// freq: child_count(t, layer) words, caller-owned
+static int histogram_into(const Tree& t, uint64_t layer, uint32_t* freq) {
   Tree& ctx = const_cast<Tree&>(t);
   const uint64_t n_child = child_count(t, layer);
-  STB_CUDA(ctx, freq.alloc(n_child, t.stream));
-  STB_CUDA(ctx, cudaMemsetAsync(freq.ptr, 0, std::max<uint64_t>(n_child, 1) * 4, t.stream));
+  STB_CUDA(ctx, cudaMemsetAsync(freq, 0, std::max<uint64_t>(n_child, 1) * 4, t.stream));
   const uint32_t n = (uint32_t)t.layers[layer].count;
   Launch l(ctx, "histogram");
-  histogram_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, t.stream>>>(t.layers[layer].nodes.ptr, n, freq.ptr);
+  histogram_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, t.stream>>>(t.layers[layer].nodes.ptr, n, freq);
   return STB_OK;
+}
+
+int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq) {
+  Tree& ctx = const_cast<Tree&>(t);
+  STB_CUDA(ctx, freq.alloc(std::max<uint64_t>(child_count(t, layer), 1), t.stream));
+  return histogram_into(t, layer, freq.ptr);
 }
 
 int histogram_u64(const Tree& t, uint64_t layer, unsigned long long* d_out) {
@@ -249,19 +255,45 @@ int sort_tree(Tree& t) {
   cudaStream_t st = t.stream;
   const size_t L = t.layers.size();
   // child layer c (0 = leaves, c>0 = node layer c-1) is referenced from node layer c.
-  std::vector<DevBuf<uint32_t>> freq(L), newpos(L);
-  DevBuf<uint32_t> d_max;
-  STB_CUDA(t, d_max.alloc(L, st));
-  STB_CUDA(t, cudaMemsetAsync(d_max.ptr, 0, L * 4, st));
+  // All scratch comes from one arena kept by the handle (grow-only): a sort allocates nothing
+  // once the handle has sorted a tree of this size.
+  uint64_t n_max = 1, arena_bytes = 0;
+  auto carve = [&](uint64_t bytes) {
+    const uint64_t off = arena_bytes;
+    arena_bytes += (bytes + 255) & ~255ull;
+    return off;
+  };
+  std::vector<uint64_t> freq_off(L), newpos_off(L);
+  const uint64_t max_off = carve(L * 4);
   for (size_t c = 0; c < L; ++c) {
-    STB_TRY(histogram_layer(t, c, freq[c]));
+    const uint64_t n = std::max<uint64_t>(child_count(t, c), 1);
+    n_max = std::max(n_max, n);
+    freq_off[c] = carve(n * 4);
+    newpos_off[c] = carve(n * 4);
+  }
+  const uint64_t nblocks_max = ceil_div(n_max, RS_TILE);
+  const uint64_t hist_off = carve(256 * nblocks_max * 4), row_off = carve(256 * 4);
+  const uint64_t ka_off = carve(n_max * 4), va_off = carve(n_max * 4), kb_off = carve(n_max * 4), vb_off = carve(n_max * 4);
+  uint64_t moved_bytes = t.n_leaves * 8;
+  for (size_t k = 0; k < L; ++k) moved_bytes = std::max<uint64_t>(moved_bytes, t.layers[k].count * sizeof(uint2));
+  const uint64_t moved_off = carve(moved_bytes);
+  STB_CUDA(t, t.sort_arena.ensure(arena_bytes, st));
+  char* arena = t.sort_arena.ptr;
+  auto words = [&](uint64_t off) { return reinterpret_cast<uint32_t*>(arena + off); };
+  std::vector<uint32_t*> freq(L), newpos(L);
+  uint32_t* d_max = words(max_off);
+  STB_CUDA(t, cudaMemsetAsync(d_max, 0, L * 4, st));
+  for (size_t c = 0; c < L; ++c) {
+    freq[c] = words(freq_off[c]);
+    newpos[c] = words(newpos_off[c]);
+    STB_TRY(histogram_into(t, c, freq[c]));
     const uint32_t n = (uint32_t)child_count(t, c);
     Launch l(t, "freq_max");
     const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(n, HS_THREADS), 1184);
-    max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c].ptr, n, d_max.ptr + c);
+    max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c], n, d_max + c);
   }
   std::vector<uint32_t> maxf(L);
-  STB_CUDA(t, cudaMemcpyAsync(maxf.data(), d_max.ptr, L * 4, cudaMemcpyDeviceToHost, st));
+  STB_CUDA(t, cudaMemcpyAsync(maxf.data(), d_max, L * 4, cudaMemcpyDeviceToHost, st));
   STB_CUDA(t, cudaStreamSynchronize(st));
 
   // ranks
@@ -272,66 +304,58 @@ int sort_tree(Tree& t) {
     for (uint32_t span = maxf[c] ? maxf[c] - 1 : 0; span; span >>= 8) ++passes;  // keys are maxf - freq in [0, maxf-1]
     if (passes == 0 || n < 2) continue;  // every frequency equal: stable sort = identity
     permuted[c] = true;
-    STB_CUDA(t, newpos[c].alloc(n, st));
     const uint32_t nblocks = (uint32_t)ceil_div(n, RS_TILE);
-    DevBuf<uint32_t> hist, row_total, keys_a, vals_a, keys_b, vals_b;
-    STB_CUDA(t, hist.alloc((uint64_t)256 * nblocks, st));
-    STB_CUDA(t, row_total.alloc(256, st));
-    if (passes > 1) {
-      STB_CUDA(t, keys_a.alloc(n, st));
-      STB_CUDA(t, vals_a.alloc(n, st));
-    }
-    if (passes > 2) {
-      STB_CUDA(t, keys_b.alloc(n, st));
-      STB_CUDA(t, vals_b.alloc(n, st));
-    }
-    const uint32_t* kin = freq[c].ptr;
+    uint32_t *hist = words(hist_off), *row_total = words(row_off);
+    uint32_t *keys_a = words(ka_off), *vals_a = words(va_off), *keys_b = words(kb_off), *vals_b = words(vb_off);
+    const uint32_t* kin = freq[c];
     const uint32_t* vin = nullptr;
     for (int p = 0; p < passes; ++p) {
       const int shift = 8 * p;
       const bool first = p == 0, last = p == passes - 1;
-      uint32_t* kout = last ? nullptr : ((p & 1) ? keys_b.ptr : keys_a.ptr);
-      uint32_t* vout = last ? newpos[c].ptr : ((p & 1) ? vals_b.ptr : vals_a.ptr);
+      uint32_t* kout = last ? nullptr : ((p & 1) ? keys_b : keys_a);
+      uint32_t* vout = last ? newpos[c] : ((p & 1) ? vals_b : vals_a);
       {
         Launch l(t, "radix_hist");
-        radix_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, maxf[c], shift, nblocks, hist.ptr);
+        radix_hist_kernel<<<nblocks, RS_THREADS, 0, st>>>(kin, n, maxf[c], shift, nblocks, hist);
       }
       {
         Launch l(t, "radix_rowscan");
-        radix_rowscan_kernel<<<256, 1024, 0, st>>>(hist.ptr, nblocks, row_total.ptr);
+        radix_rowscan_kernel<<<256, 1024, 0, st>>>(hist, nblocks, row_total);
       }
       {
         Launch l(t, "radix_scatter");
-        if (first && last) radix_scatter_kernel<true, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
-        else if (first) radix_scatter_kernel<true, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
-        else if (last) radix_scatter_kernel<false, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
-        else radix_scatter_kernel<false, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist.ptr, row_total.ptr, kout, vout);
+        if (first && last) radix_scatter_kernel<true, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist, row_total, kout, vout);
+        else if (first) radix_scatter_kernel<true, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist, row_total, kout, vout);
+        else if (last) radix_scatter_kernel<false, true><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist, row_total, kout, vout);
+        else radix_scatter_kernel<false, false><<<nblocks, RS_THREADS, 0, st>>>(kin, vin, n, maxf[c], shift, nblocks, hist, row_total, kout, vout);
       }
       kin = kout;
       vin = vout;
     }
   }
 
-  // apply: leaves, then every node layer (the top layer keeps its order, :455/:469)
+  // apply: leaves, then every node layer (the top layer keeps its order, :455/:469); permuted
+  // into the arena, then copied back over the layer's own storage
   if (permuted[0]) {
-    DevBuf<unsigned long long> moved;
-    STB_CUDA(t, moved.alloc(t.n_leaves, st));
-    Launch l(t, "permute_leaves");
-    permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0].ptr, moved.ptr);
-    t.leaves = std::move(moved);
+    unsigned long long* moved = reinterpret_cast<unsigned long long*>(arena + moved_off);
+    {
+      Launch l(t, "permute_leaves");
+      permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0], moved);
+    }
+    STB_CUDA(t, cudaMemcpyAsync(t.leaves.ptr, moved, t.n_leaves * 8, cudaMemcpyDeviceToDevice, st));
   }
   for (size_t k = 0; k < L; ++k) {
-    const uint32_t* child_map = permuted[k] ? newpos[k].ptr : nullptr;
-    const uint32_t* dst_map = (k + 1 < L && permuted[k + 1]) ? newpos[k + 1].ptr : nullptr;
+    const uint32_t* child_map = permuted[k] ? newpos[k] : nullptr;
+    const uint32_t* dst_map = (k + 1 < L && permuted[k + 1]) ? newpos[k + 1] : nullptr;
     if (!child_map && !dst_map) continue;
     const uint32_t n = (uint32_t)t.layers[k].count;
-    DevBuf<uint2> moved;
-    STB_CUDA(t, moved.alloc(n, st));
+    uint2* moved = reinterpret_cast<uint2*>(arena + moved_off);
     {
       Launch l(t, "permute_rewire");
-      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved.ptr);
+      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved);
     }
-    t.layers[k].nodes = std::move(moved);
+    Launch l(t, "permute_copy_back", false);
+    STB_CUDA(t, cudaMemcpyAsync(t.layers[k].nodes.ptr, moved, (uint64_t)n * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
   }
   t.plan_valid = false;
   STB_CUDA(t, cudaStreamSynchronize(st));

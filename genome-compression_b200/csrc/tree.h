@@ -29,12 +29,14 @@ struct Tree : Ctx {
   // repeated builds on one handle do no device allocation.
   std::shared_ptr<void> workspace;
   DevBuf<char> staging;
-  // Scratch of decode (two ping-pong pointer arrays): grow-only as well, so repeated decodes on
-  // one handle allocate nothing.
+  // Scratch of decode (two ping-pong pointer arrays) and of sort_tree (one arena carved by
+  // offsets): grow-only as well, so repeated calls on one handle allocate nothing.
   DevBuf<uint32_t> decode_a, decode_b;
+  DevBuf<char> sort_arena;
   void release_scratch() {
     decode_a.release();
     decode_b.release();
+    sort_arena.release();
   }
 
   // serialization plan cache (per-layer byte totals), invalidated by build / sort

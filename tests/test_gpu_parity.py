@@ -65,6 +65,18 @@ def full_check(stb, oracle, text_or_leaves, S, from_text=True, rec=None, what=""
     # sub-range decode
     for first, count in ((0, 1), (n - 1, 1), (n // 3, min(n - n // 3, 777)), (1, n - 1) if n > 1 else (0, 1)):
         assert np.array_equal(tree.decode(first, count), leaves[first:first + count]), (what, first, count)
+    # ... as text, into device memory at odd byte offsets (the output kernel stages whole tiles)
+    import torch
+    whole = b"".join(stb.leaf_to_str(v, S).encode() for v in leaves[:min(n, 6000)])
+    for first, count, off in ((0, min(n, 6000), 0), (min(n - 1, 5), min(n - min(n - 1, 5), 4100), 1), (min(n - 1, 2049), 1, 3),
+                              (n // 2, min(n - n // 2, 9), 2)):
+        if first + count > min(n, 6000):
+            continue
+        buf = torch.zeros(count * S + 8, dtype=torch.uint8, device="cuda")
+        tree.decode_ascii(first, count, out=buf[off:])
+        got = bytes(buf.cpu().numpy())
+        assert got[off:off + count * S] == whole[first * S:(first + count) * S], (what, first, count, off)
+        assert got[:off] == bytes(off) and got[off + count * S:] == bytes(8 - off), (what, "wrote outside the range")
     # deserialize round trip (invariant bits are not stored)
     back = stb.SharedTree(S).deserialize(post)
     assert back.width() == n and back.leaf_count() == tree.leaf_count()
