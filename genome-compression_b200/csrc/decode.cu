@@ -22,10 +22,12 @@ struct LayerPtrs {
 };
 
 // access_leaf (src/shared_tree.cpp:231-236): stored leaf -> mirrored? -> transposed?
+// mirrored = transposed(inverted) and transposed is an involution, so at most one of each is
+// ever needed: (m,t) = 00 v, 01 T(v), 10 T(I(v)), 11 I(v).
 __device__ __forceinline__ unsigned long long apply_leaf(unsigned long long v, uint32_t p, int S) {
-  if (p & MIRROR) v = leaf_mirrored(v, S);
-  if (p & TRANSPOSE) v = leaf_transposed(v);
-  return v;
+  const bool m = (p & MIRROR) != 0, t = (p & TRANSPOSE) != 0;
+  const unsigned long long x = m ? leaf_inverted(v, S) : v;
+  return m != t ? leaf_transposed(x) : x;
 }
 
 // One expansion step.  cur[] holds the pointers of node layer `k` for positions
