@@ -149,6 +149,37 @@ fused_leaves_kernel(const uint32_t* __restrict__ cur, unsigned long long lo_cur,
   });
 }
 
+// Text output, fast path (leaf size a multiple of 4, range starting at a multiple of 8 leaves,
+// 16-byte aligned destination; whole groups only): the 8 leaves of a thread are 8*S contiguous
+// bytes, spelled in registers and stored as 16-byte vectors.  No shared memory, so the L1 keeps
+// the node lines that the four strided layer-0 loads of a warp share.
+template <int S_T>
+__global__ void __launch_bounds__(DEC_THREADS)
+fused_ascii_aligned_kernel(const uint32_t* __restrict__ cur, const uint2* __restrict__ layer2, const uint2* __restrict__ layer1,
+                           const uint2* __restrict__ layer0, const unsigned long long* __restrict__ leaves,
+                           unsigned long long groups, uint4* __restrict__ out) {
+  const unsigned long long g = (unsigned long long)blockIdx.x * DEC_THREADS + threadIdx.x;
+  if (g >= groups) return;
+  unsigned long long v[FUSE_LEAVES];
+#pragma unroll
+  for (int i = 0; i < FUSE_LEAVES; ++i) v[i] = 0ull;
+  walk_subtree(cur[g], layer2, layer1, layer0, [&](uint32_t slot, uint32_t lp) {
+    const unsigned long long x = apply_leaf(__ldg(leaves + (lp & IDX_MASK)), lp, S_T);
+#pragma unroll
+    for (int i = 0; i < FUSE_LEAVES; ++i)
+      if (slot == (uint32_t)i) v[i] = x;  // slot is a compile-time constant after unrolling
+  });
+  constexpr int WORDS = S_T / 4;  // words per leaf
+  uint32_t w[FUSE_LEAVES * WORDS];
+#pragma unroll
+  for (int i = 0; i < FUSE_LEAVES; ++i)
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) w[i * WORDS + k] = nac_letters4((uint32_t)(v[i] >> (16 * k)) & 0xffffu);
+  uint4* o = out + g * (FUSE_LEAVES * WORDS / 4);
+#pragma unroll
+  for (int q = 0; q < FUSE_LEAVES * WORDS / 4; ++q) o[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
 // Text output in two phases so that both are free of bank conflicts: (1) thread t walks its
 // subtree and parks the 8 leaf values in shared memory, transposed (slot-major); (2) the
 // threads take consecutive leaves and spell them into the staged tile (word stores when the
@@ -307,8 +338,28 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
       fused_leaves_kernel<<<(unsigned)ceil_div(groups, DEC_THREADS), DEC_THREADS, 0, st>>>(cur, lo_cur, l2, l1, l0, t.leaves.ptr, t.S, first, count, d_out);
     }
     if (d_ascii) {
-      Launch l(t, "ascii_out_fused");
-      fused_ascii_kernel<<<(unsigned)ceil_div(groups, FA_THREADS), FA_THREADS, 0, st>>>(cur, lo_cur, l2, l1, l0, t.leaves.ptr, t.S, first, count, d_ascii);
+      // whole groups through the register path when the layout allows it, the rest (or everything) staged
+      uint64_t fast_groups = 0;
+      const bool aligned = (first & (FUSE_LEAVES - 1)) == 0 && (reinterpret_cast<uintptr_t>(d_ascii) & 15u) == 0;
+      if (aligned && (t.S == 4 || t.S == 8 || t.S == 12 || t.S == 16)) fast_groups = count >> FUSE;
+      if (fast_groups) {
+        Launch l(t, "ascii_out_fused_aligned");
+        const unsigned nb = (unsigned)ceil_div(fast_groups, DEC_THREADS);
+        uint4* o = reinterpret_cast<uint4*>(d_ascii);
+        if (t.S == 4) fused_ascii_aligned_kernel<4><<<nb, DEC_THREADS, 0, st>>>(cur, l2, l1, l0, t.leaves.ptr, fast_groups, o);
+        else if (t.S == 8) fused_ascii_aligned_kernel<8><<<nb, DEC_THREADS, 0, st>>>(cur, l2, l1, l0, t.leaves.ptr, fast_groups, o);
+        else if (t.S == 12) fused_ascii_aligned_kernel<12><<<nb, DEC_THREADS, 0, st>>>(cur, l2, l1, l0, t.leaves.ptr, fast_groups, o);
+        else fused_ascii_aligned_kernel<16><<<nb, DEC_THREADS, 0, st>>>(cur, l2, l1, l0, t.leaves.ptr, fast_groups, o);
+      }
+      const uint64_t done = fast_groups << FUSE;
+      if (done < count) {
+        Launch l(t, "ascii_out_fused");
+        const uint64_t rest_first = first + done, rest = count - done;
+        const uint64_t rest_groups = (last >> FUSE) - (rest_first >> FUSE) + 1;
+        fused_ascii_kernel<<<(unsigned)ceil_div(rest_groups, FA_THREADS), FA_THREADS, 0, st>>>(
+            cur + ((rest_first >> FUSE) - lo_cur), rest_first >> FUSE, l2, l1, l0, t.leaves.ptr, t.S, rest_first, rest,
+            d_ascii + done * (uint64_t)t.S);
+      }
     }
   } else {
     if (d_out) {
