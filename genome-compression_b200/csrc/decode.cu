@@ -149,6 +149,28 @@ fused_leaves_kernel(const uint32_t* __restrict__ cur, unsigned long long lo_cur,
   });
 }
 
+// Packed leaves, fast path (range starting at a multiple of 8 leaves, 16-byte aligned
+// destination, whole groups): 64 contiguous bytes per thread as four 16-byte stores.
+__global__ void __launch_bounds__(DEC_THREADS)
+fused_leaves_aligned_kernel(const uint32_t* __restrict__ cur, const uint2* __restrict__ layer2, const uint2* __restrict__ layer1,
+                            const uint2* __restrict__ layer0, const unsigned long long* __restrict__ leaves, int S,
+                            unsigned long long groups, ulonglong2* __restrict__ out) {
+  const unsigned long long g = (unsigned long long)blockIdx.x * DEC_THREADS + threadIdx.x;
+  if (g >= groups) return;
+  unsigned long long v[FUSE_LEAVES];
+#pragma unroll
+  for (int i = 0; i < FUSE_LEAVES; ++i) v[i] = 0ull;
+  walk_subtree(cur[g], layer2, layer1, layer0, [&](uint32_t slot, uint32_t lp) {
+    const unsigned long long x = apply_leaf(__ldg(leaves + (lp & IDX_MASK)), lp, S);
+#pragma unroll
+    for (int i = 0; i < FUSE_LEAVES; ++i)
+      if (slot == (uint32_t)i) v[i] = x;
+  });
+  ulonglong2* o = out + g * (FUSE_LEAVES / 2);
+#pragma unroll
+  for (int q = 0; q < FUSE_LEAVES / 2; ++q) o[q] = make_ulonglong2(v[2 * q], v[2 * q + 1]);
+}
+
 // Text output, fast path (leaf size a multiple of 4, range starting at a multiple of 8 leaves,
 // 16-byte aligned destination; whole groups only): the 8 leaves of a thread are 8*S contiguous
 // bytes, spelled in registers and stored as 16-byte vectors.  No shared memory, so the L1 keeps
@@ -334,8 +356,21 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
     const uint64_t groups = (last >> FUSE) - (first >> FUSE) + 1;
     const uint2 *l2 = t.layers[2].nodes.ptr, *l1 = t.layers[1].nodes.ptr, *l0 = t.layers[0].nodes.ptr;
     if (d_out) {
-      Launch l(t, "leaves_out_fused");
-      fused_leaves_kernel<<<(unsigned)ceil_div(groups, DEC_THREADS), DEC_THREADS, 0, st>>>(cur, lo_cur, l2, l1, l0, t.leaves.ptr, t.S, first, count, d_out);
+      const bool aligned = (first & (FUSE_LEAVES - 1)) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
+      const uint64_t fast_groups = aligned ? count >> FUSE : 0;
+      if (fast_groups) {
+        Launch l(t, "leaves_out_fused_aligned");
+        fused_leaves_aligned_kernel<<<(unsigned)ceil_div(fast_groups, DEC_THREADS), DEC_THREADS, 0, st>>>(
+            cur, l2, l1, l0, t.leaves.ptr, t.S, fast_groups, reinterpret_cast<ulonglong2*>(d_out));
+      }
+      const uint64_t done = fast_groups << FUSE;
+      if (done < count) {
+        Launch l(t, "leaves_out_fused");
+        const uint64_t rest_first = first + done, rest = count - done;
+        const uint64_t rest_groups = (last >> FUSE) - (rest_first >> FUSE) + 1;
+        fused_leaves_kernel<<<(unsigned)ceil_div(rest_groups, DEC_THREADS), DEC_THREADS, 0, st>>>(
+            cur + ((rest_first >> FUSE) - lo_cur), rest_first >> FUSE, l2, l1, l0, t.leaves.ptr, t.S, rest_first, rest, d_out + done);
+      }
     }
     if (d_ascii) {
       // whole groups through the register path when the layout allows it, the rest (or everything) staged
