@@ -471,8 +471,12 @@ def run_b200_dist(args, world, rank, local_rank):
         tree = builder.build_from_body(body, n_bases)
     torch.cuda.synchronize()
     dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # rank 0 alone polls NVML, and sparsely (its GPU's clocks go into the line): eight processes
+    # polling every 4 ms contend for the driver and doubled the step time at N = 8 (13.7 against
+    # 6.1 ms); the timed region lasts >= 30 ms, so 12 ms still puts samples inside it
+    sampler = ClockSampler(local_rank, period_s=0.012) if rank == 0 else None
+    if sampler:
+        sampler.start()
     launches0 = pkg.kernel_launches()
     stages.ctx.profile(True)
     stages.ctx.profile_reset()
@@ -486,7 +490,7 @@ def run_b200_dist(args, world, rank, local_rank):
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([pkg.kernel_launches() - launches0], device="cuda", dtype=torch.int64)
