@@ -353,7 +353,6 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
     lo_cur = lo_next;
   }
   if (stop) {
-    const uint64_t groups = (last >> FUSE) - (first >> FUSE) + 1;
     const uint2 *l2 = t.layers[2].nodes.ptr, *l1 = t.layers[1].nodes.ptr, *l0 = t.layers[0].nodes.ptr;
     if (d_out) {
       const bool aligned = (first & (FUSE_LEAVES - 1)) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;

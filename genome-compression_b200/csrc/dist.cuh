@@ -41,44 +41,6 @@ __device__ __forceinline__ void produce(const void* items, uint64_t n_items, int
   }
 }
 
-// one CTA per owner: exclusive scan of its row + row total
-static __global__ void __launch_bounds__(1024) rowscan_kernel(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ row_total) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < nblocks; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nblocks ? row[i] : 0u;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t before = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - v;
-    if (i < nblocks) row[i] = before;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = before + v;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) row_total[blockIdx.x] = carry_s;
-}
-
 constexpr uint32_t OWNER_SINGLETON = 0xffffffffu;  // slot marker: certified singleton, never in the table
 
 __device__ __forceinline__ void owner_filter_cell(unsigned long long key, uint32_t log2_bits, uint32_t& word, uint32_t& bit) {

@@ -394,7 +394,6 @@ int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas,
   STB_TRY(peer_bases(t, world, arenas, peers));
   const ArenaLayout L = arena_layout(world, region_cap);
   const char* mine = peers.base[rank];
-  const PeerHdr* hdr = reinterpret_cast<const PeerHdr*>(mine + L.hdr);
   // grids: sized for the expected share, grid-stride for whatever actually arrived
   const uint64_t expect = std::max<uint64_t>(expected_records, 1024);
   const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(expect, 1024) + 64, 1u << 20);
