@@ -388,7 +388,7 @@ int stb_dist_peer_owner(stb_tree* ctx, int world, int rank, void* const* arenas,
   Tree& t = *ctx;
   cudaStream_t st = t.stream;
   const uint64_t worst = (uint64_t)world * region_cap;  // every record of the level lands here
-  if (2 * worst > 0x1ffffffeull) return t.fail(STB_ERR_TOO_LARGE, "level too large for one owner table");
+  if (2 * worst >= 0xffffffffull) return t.fail(STB_ERR_TOO_LARGE, "level too large for one owner table");  // 32-bit slot numbers
   if (table_slots < std::max<uint64_t>(1024, 2 * worst) + 1) return t.fail(STB_ERR_BUFFER_TOO_SMALL, "owner table smaller than 2 * world * region_cap + 1 slots");
   PeerBases peers;
   STB_TRY(peer_bases(t, world, arenas, peers));
