@@ -4,11 +4,17 @@ One process per GPU; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is 
 plumbing, the stage kernels of include/shared_tree_b200_dist.h are the work.  Protocol
 per level (leaves, then node layers bottom-up):
 
-    partition by hash owner -> all_to_all(keys, positions) -> owner dedups with min global
-    position, answers every record, marks first occurrences in a bitmap -> all_to_all(answers),
-    all_reduce(bitmap) -> rank index -> ids = rank of the first occurrence's bit
+    every (key, global position) record goes to the key's hash owner -> the owner dedups with
+    min global position, tells the source where the key came first, marks first occurrences in
+    a bitmap -> all_reduce(bitmap) -> rank index -> ids = rank of the first occurrence's bit
 
-so node ids are first-occurrence ranks in GLOBAL position order: identical to the single-GPU
+The records travel either through peer-mapped memory — the stage kernels store them straight
+into the owner's arena over NVLink and the owner stores the answers back; two small
+collectives per level, nothing read by the host (exchange="peer", the default on one node) —
+or through all_to_all collectives (exchange="collective": other transports, the CPU tests,
+and the joint fallback when peer mapping is unavailable).
+
+Node ids are first-occurrence ranks in GLOBAL position order: identical to the single-GPU
 build and to the reference (src/shared_tree.cpp:630-637, :662-672).  Rank g owns a contiguous
 power-of-two aligned range of positions at every sharded level (the analogue of the
 reference's 2^22-leaf segments, include/shared_tree.h:305-316); when a level is small the
@@ -426,7 +432,6 @@ class DistBuilder:
         assert exchange in ("peer", "collective"), exchange
         self.exchange = exchange
         self.peer = None
-        self._pending = []
         self.collectives = 0
         self.trace = bool(int(os.environ.get("STB_DIST_TRACE", "0")))
         self._t0 = time.perf_counter()
