@@ -319,6 +319,50 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict_
   if (threadIdx.x == 0) *total_out = carry_s;
 }
 
+// Large levels: one CTA per chunk of 1024 * SCAN_PER_THREAD counts scans its chunk in place
+// (exclusive, from 0) and leaves the chunk total in chunk_sum[]; scan_blocks_kernel then scans
+// the few chunk totals, and assign_kernel adds its chunk's base.  The single-CTA loop over a
+// 3.1 Gbp leaf level is 16 dependent rounds; this is one.
+constexpr uint32_t SCAN_CHUNK = 1024 * SCAN_PER_THREAD;
+constexpr uint32_t SCAN_MAX_CHUNKS = 1024;
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(uint32_t* __restrict__ cnt, uint32_t nb, uint32_t* __restrict__ chunk_sum) {
+  __shared__ uint32_t warp_sum[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+  uint32_t v[SCAN_PER_THREAD];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+    v[j] = i0 + j < nb ? cnt[i0 + j] : 0u;
+    sum += v[j];
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_sum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += y;
+    }
+    warp_sum[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = (warp ? warp_sum[warp - 1] : 0u) + x - sum;
+#pragma unroll
+  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
+    if (i0 + j < nb) cnt[i0 + j] = run;
+    run += v[j];
+  }
+  if (threadIdx.x == 1023) chunk_sum[blockIdx.x] = run;
+}
+
 enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
 
 // First occurrences: id = rank in position order; append the item to its layer in id order
@@ -328,7 +372,8 @@ template <int MODE>
 __global__ void __launch_bounds__(LVL_THREADS)
 assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
               const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S,
-              const uint32_t* __restrict__ children, uint32_t n_children, uint32_t first_block) {
+              const uint32_t* __restrict__ children, uint32_t n_children, uint32_t first_block,
+              const uint32_t* __restrict__ chunk_base = nullptr) {
   __shared__ uint32_t word_pref[32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t block = first_block + blockIdx.x;
@@ -351,7 +396,7 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
     word_pref[lane] = x - v;
   }
   __syncthreads();
-  const uint32_t base = blockbase[block];
+  const uint32_t base = blockbase[block] + (chunk_base ? chunk_base[block / SCAN_CHUNK] : 0u);
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
     const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
@@ -417,7 +462,7 @@ struct LeafInput {
 };
 
 struct Scratch {
-  DevBuf<uint32_t> ptr_a, ptr_b, bitmask, blockcnt, counts, dminpos, dids;
+  DevBuf<uint32_t> ptr_a, ptr_b, bitmask, blockcnt, chunk_sum, counts, dminpos, dids;
   DevBuf<Slot> slots;
   DevBuf<BuildFlags> flags;
   DevBuf<uint32_t> root;
@@ -473,13 +518,24 @@ void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& 
     Launch l(ctx, "bitmask_blockcnt");
     bitmask_blockcnt_kernel<<<(unsigned)ceil_div((uint64_t)nb * 32, 256), 256, 0, ctx.stream>>>(sc.bitmask.ptr, nb, sc.blockcnt.ptr);
   }
-  {
+  const uint32_t* chunk_base = nullptr;
+  if (nb > SCAN_CHUNK && sc.chunk_sum.ptr) {  // two levels: chunks in parallel, then their (few) totals
+    const unsigned nchunks = (unsigned)ceil_div(nb, SCAN_CHUNK);
+    {
+      Launch l(ctx, "scan_blocks");
+      scan_chunks_kernel<<<nchunks, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, sc.chunk_sum.ptr);
+    }
+    Launch l(ctx, "scan_blocks");
+    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.chunk_sum.ptr, nchunks, total_out, nullptr);
+    chunk_base = sc.chunk_sum.ptr;
+  } else {
     Launch l(ctx, "scan_blocks");
     scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, total_out, nullptr);
   }
   {
     Launch l(ctx, "assign_ids");
-    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children, 0u);
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children, 0u,
+                                                            chunk_base);
   }
   {
     Launch l(ctx, "resolve_ids");
@@ -719,6 +775,7 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   STB_CUDA(t, sc.ptr_b.ensure(n1, st));
   STB_CUDA(t, sc.bitmask.ensure(ceil_div(n0, LVL_TILE) * (LVL_TILE / 32), st));
   STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n0, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
   STB_CUDA(t, sc.counts.ensure(80, st));
   STB_CUDA(t, sc.flags.ensure(1, st));
   STB_CUDA(t, sc.root.ensure(1, st));
@@ -920,6 +977,7 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
   STB_CUDA(t, sc.ptr_b.ensure(ceil_div(n_top, 2), st));
   STB_CUDA(t, sc.bitmask.ensure(ceil_div(n_top, LVL_TILE) * (LVL_TILE / 32), st));
   STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n_top, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
   STB_CUDA(t, sc.filter.ensure(filter_words(ceil_div(n_top, 2)), st));
   {
     bool grew = false;
@@ -969,6 +1027,7 @@ int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_leas
   STB_CUDA(t, sc.ptr_b.ensure(n1, st));
   STB_CUDA(t, sc.bitmask.ensure(ceil_div(n1, LVL_TILE) * (LVL_TILE / 32), st));
   STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n1, LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
   STB_CUDA(t, sc.counts.ensure(80, st));
   STB_CUDA(t, sc.filter.ensure(filter_words(n1), st));
   {

@@ -240,7 +240,7 @@ def test_synthetic_tree_parity(stb, oracle):
 def test_large_properties(stb):
     """Sizes the oracle would not finish quickly: size-independent properties only."""
     import torch
-    n = 200_000_000
+    n = 260_000_000  # leaf level > 16384 CTA tiles: the two-level scan runs
     buf = torch.empty(n, dtype=torch.uint8, device="cuda")
     stb.synth_genome(buf, n, seed=1, repeat_permille=500)
     tree = stb.SharedTree(12).build_from_body(buf)
