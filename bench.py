@@ -416,7 +416,8 @@ def run_b200(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels, "pipeline": pipeline,
-        "tree": {"width": n0, "leaves": tree.leaf_count(), "nodes": tree.node_count(), "depth": tree.depth()},
+        "tree": {"width": n0, "leaves": tree.leaf_count(), "nodes": tree.node_count(), "depth": tree.depth(),
+                 "first_layer_nodes": [int(c) for c in counts[:6]]},  # compare with "sharded_layer_nodes" of the N > 1 lines
     }
     print(json.dumps(line), flush=True)
 
