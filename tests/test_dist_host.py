@@ -99,6 +99,18 @@ def test_shard_plan():
     assert tiny.sharded_levels() == 1 and tiny.level_range(0, 0) == (0, 1) and tiny.level_range(3, 0) == (1, 1)
 
 
+def test_default_cut_follows_world(monkeypatch):
+    load_package()
+    from genome_compression_b200.dist import ShardPlan, default_cut
+    monkeypatch.delenv("STB_DIST_CUT_LOG2", raising=False)
+    assert [default_cut(w) for w in (1, 2, 4, 8, 16, 64)] == [1 << 25, 1 << 24, 1 << 23, 1 << 22, 1 << 21, 1 << 20]
+    # config 4 on 8 ranks: leaf level + 5 node levels sharded, the 4.0 M-position level goes to rank 0
+    plan = ShardPlan(258_333_333, 8)
+    assert plan.cut == 1 << 22 and plan.sharded_levels() == 6
+    monkeypatch.setenv("STB_DIST_CUT_LOG2", "18")
+    assert default_cut(8) == 1 << 18 and ShardPlan(258_333_333, 8).sharded_levels() == 10
+
+
 def test_thread_comm_virtual_ranks(oracle):
     """The in-process communicator used on single-GPU boxes, here with the numpy stages."""
     import threading
