@@ -98,6 +98,7 @@ class DistTree:
     layer_totals: list    # global unique count per sharded layer (leaf level first)
     upper: object         # rank 0: stages' upper-tree object, else None
     root: int | None
+    build_id: int = 0     # the builder's build counter: rank 0's top layers live in a handle the next build reuses
 
 
 class CudaStages:
@@ -432,6 +433,7 @@ class DistBuilder:
         assert exchange in ("peer", "collective"), exchange
         self.exchange = exchange
         self.peer = None
+        self.builds = 0
         self.collectives = 0
         self.trace = bool(int(os.environ.get("STB_DIST_TRACE", "0")))
         self._t0 = time.perf_counter()
@@ -649,7 +651,8 @@ class DistBuilder:
                 raise OverflowError("a layer outgrew the 29-bit pointer index (src/shared_tree.cpp:54-67)")
             slices.append(LayerSlice(base, count, items[:count]))
             totals.append(total)
-        return DistTree(self.st.dna_size, n_leaves_total, slices[0], slices[1:], totals, upper, root)
+        self.builds += 1
+        return DistTree(self.st.dna_size, n_leaves_total, slices[0], slices[1:], totals, upper, root, self.builds)
 
     def build_from_body(self, local_body, n_bases_total: int) -> DistTree:
         """local_body: uint8 device tensor holding the bases of this rank's leaf range."""
@@ -667,7 +670,10 @@ class DistBuilder:
 
     def gather(self, tree: DistTree):
         """Collects every slice on rank 0 and assembles an ordinary SharedTree there
-        (None on the other ranks).  Untimed in bench.py: only needed to serialize / verify."""
+        (None on the other ranks).  Untimed in bench.py: only needed to serialize / verify.
+        Must be called before the builder's next build (which reuses rank 0's top-layer handle)."""
+        if tree.build_id != self.builds:
+            raise ValueError("gather() needs the result of this builder's latest build")
         def gather_slice(sl):
             counts = self.comm.all_gather_object(sl.count)
             return self._gather_rows(sl.items.contiguous(), counts, dst=0)

@@ -173,6 +173,10 @@ def test_peer_exchange_orchestration_virtual_ranks(oracle, world, n, S, cut, tex
                     tree = builder.build_from_leaves(torch.from_numpy(leaves[lo:hi].view(np.int64).copy()), n)
             out[rank] = (builder.gather(tree), tree.layer_totals)
             collectives[rank] = builder.collectives
+            stale = tree
+            tree = builder.build_from_leaves(torch.from_numpy(leaves[lo:hi].view(np.int64).copy()), n)
+            with pytest.raises(ValueError):
+                builder.gather(stale)  # rank 0's top layers were rebuilt by the later build
             builder.close()
         except Exception as e:  # noqa: BLE001
             errors.append(e)
