@@ -48,3 +48,51 @@ def test_random_trees(oracle, ref):
         assert np.array_equal(to.decode(), leaves) and np.array_equal(tr.decode(), leaves)
         idx = rng.integers(0, n, 500).astype(np.uint64)
         assert np.array_equal(to.random_access(idx), tr.random_access(idx))
+
+
+def _random_fasta(rng, n_bases, alphabet, width, records, blank_lines):
+    """Valid FASTA text as the reference accepts it (src/fasta_reader.cpp:40-68): a header or a
+    blank line is never followed directly by another one (the reference would parse the second
+    as data and exit on '>'), no '\\r', symbols from its table only, mixed case."""
+    letters = np.frombuffer(alphabet, dtype=np.uint8)
+    body = letters[rng.integers(0, len(letters), n_bases)].copy()
+    lower = rng.integers(0, 2, n_bases).astype(bool)
+    body[lower] = np.char.lower(body[lower].view("S1")).view(np.uint8)
+    body = body.tobytes()
+    cuts = sorted(set(int(c) for c in rng.integers(1, max(2, n_bases), records - 1))) if records > 1 and n_bases > 2 else []
+    pieces, start = [], 0
+    for k, end in enumerate(cuts + [n_bases]):
+        pieces.append(b">record %d some description\n" % k)
+        chunk = body[start:end]
+        lines = [chunk[i:i + width] for i in range(0, len(chunk), width)] or [b""]
+        for j, line in enumerate(lines):
+            pieces.append(line + b"\n")
+            if blank_lines and line and j + 1 < len(lines) and rng.integers(0, 7) == 0:
+                pieces.append(b"\n")  # a blank line between two data lines is skipped like a header
+        start = end
+    text = b"".join(pieces)
+    return text if rng.integers(0, 2) else text.rstrip(b"\n")  # with and without the final newline
+
+
+def test_fasta_ingest_fuzz(oracle, ref, tmp_path):
+    """Body extraction + packing + whole build from a FILE through the reference's own reader
+    (fasta_reader + read_genome / shared_tree{path}) against the restatement on the same bytes."""
+    rng = np.random.default_rng(10)
+    acgt, iupac = b"ACGT", b"ACGTRYKMSWBDHVN-"
+    cases = [(12, 5000, acgt, 60, 1, False), (12, 70001, acgt, 70, 3, True), (5, 3333, iupac, 50, 4, True), (16, 4096, iupac, 61, 2, False),
+             (1, 257, acgt, 7, 2, True), (13, 999, iupac, 1, 1, False), (12, 11, acgt, 80, 1, False), (12, 12, acgt, 5, 2, True),
+             (8, 40000, acgt, 100000, 1, False), (12, 25, iupac, 3, 5, True)]
+    for k, (S, n_bases, alphabet, width, records, blanks) in enumerate(cases):
+        if n_bases < S:
+            continue  # undefined in the reference (SIGFPE)
+        text = _random_fasta(rng, n_bases, alphabet, width, records, blanks)
+        path = tmp_path / f"case{k}.fa"
+        path.write_bytes(text)
+        want = ref.read_genome(path, S)
+        got = oracle.fasta_to_leaves(text, S)
+        assert len(got) == len(want) and np.array_equal(got, want), (k, S, n_bases, len(got), len(want))
+        if len(want):
+            tr, to = ref.build_file(path, S), oracle.build(got, S)
+            assert to.serialize() == tr.serialize(), (k, "pre-sort stream")
+            to.sort(); tr.sort()
+            assert to.serialize() == tr.serialize(), (k, "post-sort stream")
