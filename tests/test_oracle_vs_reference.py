@@ -43,8 +43,13 @@ def test_random_trees(oracle, ref):
         assert to.serialize() == tr.serialize()
         for k in range(to.depth() - 1):
             assert np.array_equal(to.layer(k), tr.layer(k))
+            assert np.array_equal(to.histogram(k), tr.histogram(k)), ("histogram", k)  # src/shared_tree.cpp:316
+        assert to.bytes() == tr.bytes() == len(to.serialize())
         to.sort(); tr.sort()
         assert to.serialize() == tr.serialize()
+        assert to.bytes() == tr.bytes() == len(to.serialize())
+        back = oracle.deserialize(tr.serialize(), S)  # the reference's stream parsed by the restatement
+        assert back.width() == n and np.array_equal(back.decode(), leaves)
         assert np.array_equal(to.decode(), leaves) and np.array_equal(tr.decode(), leaves)
         idx = rng.integers(0, n, 500).astype(np.uint64)
         assert np.array_equal(to.random_access(idx), tr.random_access(idx))
