@@ -62,6 +62,8 @@ def _load() -> C.CDLL:
         "stb_destroy": [vp],
         "stb_clone": [vp, P(vp)],
         "stb_release_workspace": [vp],
+        "stb_set_option": [vp, cp, u64],
+        "stb_get_option": [vp, cp, P(u64)],
         "stb_build_from_fasta": [vp, vp, u64, i32],
         "stb_build_from_body": [vp, vp, u64, i32],
         "stb_build_from_leaves": [vp, vp, u64, i32],
@@ -184,6 +186,14 @@ class SharedTree:
         out = C.c_uint64(0)
         self._check(fn(self._h, *args, C.byref(out)))
         return int(out.value)
+
+    def set_option(self, name: str, value: int) -> "SharedTree":
+        """Thresholds between the build's code paths (include/shared_tree_b200.h: stb_set_option)."""
+        self._check(lib.stb_set_option(self._h, name.encode(), int(value)))
+        return self
+
+    def get_option(self, name: str) -> int:
+        return self._u64(lib.stb_get_option, name.encode())
 
     # -- construction (shared_tree ctors, src/shared_tree.cpp:207-215) -----------------
     def build_from_fasta(self, text) -> "SharedTree":
@@ -330,6 +340,20 @@ def synth_genome(out_device_tensor, n_bases: int, first: int = 0, count: int | N
     if st != 0:
         raise StbError(st, lib.stb_status_string(st).decode())
     return out_device_tensor
+
+
+def query_indices(seed: int, queries: int, width: int) -> np.ndarray:
+    """The seeded leaf indices of BASELINE.json config 5: idx[i] = splitmix64(seed + (i + 1) * golden) mod width.
+    A closed form so that the reference's answers (tests/golden/synth.json, oracle/gen_golden_synth.py) can be
+    compared on any machine."""
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) + (np.arange(1, queries + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return (x % np.uint64(width)).astype(np.uint64)
 
 
 def leaf_to_str(v: int, dna_size: int) -> str:

@@ -1,0 +1,305 @@
+// bucket.cu — on-chip deduplication of one node level (tree_constructor::emplace_node,
+// reference src/shared_tree.cpp:662-672, for every position of reduce_nodes, :697-712).
+//
+// The keys of the first node layer are pairs of leaf ids: no locality, so a hash table in HBM
+// costs one random 128-byte line per touch and B200 does only 22-25 G of those per second
+// (profiles/microbench).  Here the table never leaves the chip:
+//
+//   partition 1   every position canonicalises its node (include/shared_tree.h:115-126) and
+//                 appends the record (key64, position32) to one of 2^b1 buckets chosen by the
+//                 top bits of the key's hash; a CTA groups its tile by bucket in shared memory
+//                 and writes whole runs                                   [HBM stream]
+//   partition 2   every first-pass bucket is split again by the next b2 hash bits, so a final
+//                 bucket holds ~2 K records                               [HBM stream]
+//   dedup         one CTA per final bucket: records -> shared memory, open-addressing table in
+//                 shared memory, min-position per key.  A record that is not its key's minimum
+//                 is a later occurrence: its first-occurrence bit is cleared and the position of
+//                 the first occurrence is OR-ed into aux[position]; a first occurrence whose key
+//                 occurs again is marked in the level's `multi` bitmap (the exact singleton
+//                 filter of the level above reads it).                    [HBM stream + sparse REDs]
+//
+// Nothing depends on the order in which records reach a bucket: ids are assigned afterwards from
+// the first-occurrence bitmap in position order (build.cu), exactly the reference's emplace order.
+// A bucket that outgrows its region raises *overflow; the dedup kernel then does nothing and
+// build.cu re-runs the level through the hash table in HBM.
+#include "bucket.cuh"
+
+namespace stb {
+
+namespace {
+
+constexpr int PT_THREADS = 512;
+constexpr int PT_ITEMS = 8;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // records per CTA tile
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_MAX_BUCKETS = 512;             // at most 9 bits per pass
+
+constexpr int DD_THREADS = 256;
+constexpr int DD_CAP = 4096;                    // records of a final bucket held in shared memory
+constexpr int DD_ITEMS = DD_CAP / DD_THREADS;
+constexpr int DD_SLOTS = 8192;
+constexpr size_t PT_SMEM = (size_t)PT_TILE * 12 + 3 * PT_MAX_BUCKETS * 4;
+constexpr size_t DD_SMEM = (size_t)DD_CAP * 12 + (size_t)DD_SLOTS * 8;
+
+__device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key) {
+  const unsigned long long h = mix64(key);
+  return h ^ (h >> 29);
+}
+
+// One partition pass.  FROM_CHILDREN: the records are made here, from the child pointer array of
+// the level (position p pairs cur[2p], cur[2p+1]; odd tail -> node{last, nullptr}, utility.h:17-29);
+// otherwise blockIdx.y names the first-pass bucket whose records are split.
+template <bool FROM_CHILDREN>
+__global__ void __launch_bounds__(PT_THREADS)
+partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
+                 const unsigned long long* __restrict__ in_keys, const uint32_t* __restrict__ in_pos,
+                 const uint32_t* __restrict__ in_count, uint32_t in_cap,
+                 unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
+                 uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
+                 const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi, uint32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)PT_TILE * 8);
+  uint32_t* hist = spos + PT_TILE;
+  uint32_t* loff = hist + PT_MAX_BUCKETS;
+  uint32_t* goff = loff + PT_MAX_BUCKETS;
+  __shared__ uint32_t warp_sum[PT_WARPS];
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nb = 1u << bits;
+  uint32_t count, first;
+  uint64_t in_base = 0;
+  if (FROM_CHILDREN) {
+    count = n_next;
+    first = blockIdx.x * PT_TILE;
+  } else {
+    count = min(__ldg(in_count + blockIdx.y), in_cap);
+    first = blockIdx.x * PT_TILE;
+    if (first >= count) return;
+    in_base = (uint64_t)blockIdx.y * in_cap;
+  }
+  for (uint32_t i = tid; i < nb; i += PT_THREADS) hist[i] = 0;
+  __syncthreads();
+
+  unsigned long long key[PT_ITEMS];
+  uint32_t pos[PT_ITEMS], dr[PT_ITEMS];
+#pragma unroll
+  for (int it = 0; it < PT_ITEMS; ++it) {
+    const uint32_t i = first + it * PT_THREADS + tid;
+    bool valid = i < count;
+    dr[it] = 0xffffffffu;
+    if (FROM_CHILDREN) {
+      pos[it] = i;
+      // every position starts as a first occurrence; the dedup kernel clears the later ones
+      const uint32_t word = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0 && word) first_bits[i >> 5] = word;
+      if (valid && child_first) {  // a child that never repeats: the only node with that child, no record
+        const uint32_t repeats = ~__ldg(child_first + (i >> 4)) | __ldg(child_multi + (i >> 4));
+        valid = ((repeats >> ((2u * i) & 31u)) & 3u) == 3u;
+      }
+      if (valid) {
+        uint32_t l, r, cl, cr, f;
+        if (2 * (uint64_t)i + 1 < n_cur) {
+          const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + i);
+          l = pr.x;
+          r = pr.y;
+        } else {
+          l = cur[2 * (uint64_t)i];
+          r = PTR_NULL;
+        }
+        canonical_node(l, r, cl, cr, f);
+        key[it] = pair_key(cl, cr);
+        aux[i] = f;  // flags at bits 29..31; the dedup kernel ORs the first occurrence's position below them
+      }
+    } else if (valid) {
+      key[it] = __ldcs(in_keys + in_base + i);
+      pos[it] = __ldcs(in_pos + in_base + i);
+    }
+    if (valid) {
+      const uint32_t d = (uint32_t)(bucket_hash(key[it]) >> shift) & (nb - 1u);
+      dr[it] = (d << 16) | atomicAdd(&hist[d], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the tile's bucket counts; one global reservation per bucket
+  {
+    const uint32_t c = tid < nb ? hist[tid] : 0u;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    if (tid < nb) {
+      loff[tid] = before + x - c;
+      uint32_t g = 0;
+      if (c) {
+        const uint32_t bucket = FROM_CHILDREN ? tid : ((blockIdx.y << bits) | tid);
+        g = atomicAdd(out_count + bucket, c);
+        if (g + c > out_cap) *overflow = 1u;
+      }
+      goff[tid] = g;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < PT_ITEMS; ++it) {
+    if (dr[it] != 0xffffffffu) {
+      const uint32_t at = loff[dr[it] >> 16] + (dr[it] & 0xffffu);
+      skey[at] = key[it];
+      spos[at] = pos[it];
+    }
+  }
+  __syncthreads();
+  // a warp writes one bucket's run at a time
+  for (uint32_t d = warp; d < nb; d += PT_WARPS) {
+    const uint32_t c = hist[d];
+    if (c == 0) continue;
+    const uint32_t g = goff[d], src = loff[d];
+    const uint32_t room = g < out_cap ? out_cap - g : 0u;
+    const uint32_t ok = min(c, room);
+    const uint32_t bucket = FROM_CHILDREN ? d : ((blockIdx.y << bits) | d);
+    const uint64_t dst = (uint64_t)bucket * out_cap + g;
+    for (uint32_t i = lane; i < ok; i += 32) {
+      out_keys[dst + i] = skey[src + i];
+      out_pos[dst + i] = spos[src + i];
+    }
+  }
+}
+
+// One CTA per final bucket.
+__global__ void __launch_bounds__(DD_THREADS)
+bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ counts,
+                    uint32_t cap, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits,
+                    const uint32_t* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
+  uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)DD_CAP * 8);
+  uint32_t* towner = spos + DD_CAP;   // record that claimed the slot (bit 31: the key occurred again)
+  uint32_t* tmin = towner + DD_SLOTS; // smallest position of the slot's key
+  if (*overflow) return;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
+  if (count == 0) return;
+  const uint64_t base = (uint64_t)blockIdx.x * cap;
+
+  unsigned long long key[DD_ITEMS];
+  uint32_t pos[DD_ITEMS];
+#pragma unroll
+  for (int j = 0; j < DD_ITEMS; ++j) {
+    const uint32_t i = j * DD_THREADS + tid;
+    if (i < count) {
+      key[j] = __ldcs(keys + base + i);
+      pos[j] = __ldcs(poss + base + i);
+    }
+  }
+  for (uint32_t i = tid; i < DD_SLOTS; i += DD_THREADS) {
+    towner[i] = 0xffffffffu;
+    tmin[i] = 0xffffffffu;
+  }
+#pragma unroll
+  for (int j = 0; j < DD_ITEMS; ++j) {
+    const uint32_t i = j * DD_THREADS + tid;
+    if (i < count) skey[i] = key[j];
+  }
+  __syncthreads();
+  uint32_t slot[DD_ITEMS];
+#pragma unroll
+  for (int j = 0; j < DD_ITEMS; ++j) {
+    const uint32_t i = j * DD_THREADS + tid;
+    if (i >= count) continue;
+    uint32_t h = (uint32_t)bucket_hash(key[j]) & (DD_SLOTS - 1);
+    for (;;) {
+      uint32_t o = towner[h];
+      if (o == 0xffffffffu) o = atomicCAS(&towner[h], 0xffffffffu, i);
+      if (o == 0xffffffffu) break;  // claimed
+      if (skey[o & 0x7fffffffu] == key[j]) {
+        if (!(o >> 31)) atomicOr(&towner[h], 0x80000000u);
+        break;
+      }
+      h = (h + 1) & (DD_SLOTS - 1);
+    }
+    atomicMin(&tmin[h], pos[j]);
+    slot[j] = h;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < DD_ITEMS; ++j) {
+    const uint32_t i = j * DD_THREADS + tid;
+    if (i >= count) continue;
+    const uint32_t p = pos[j], fp = tmin[slot[j]];
+    if (fp != p) {  // a later occurrence: not a first, and it points at the first
+      atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
+      atomicOr(aux + p, fp);
+    } else if (towner[slot[j]] >> 31) {
+      atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
+    }
+  }
+}
+
+}  // namespace
+
+BucketPlan bucket_plan(uint64_t n, const Options& opt) {
+  BucketPlan pl;
+  pl.n = n;
+  pl.cap2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(opt.bucket_cap, 16), DD_CAP);
+  // mean final bucket = half the capacity or less
+  int bits = 2;
+  while (bits < 18 && (n >> bits) > pl.cap2 / 2) ++bits;
+  pl.b1 = (bits + 1) / 2;
+  pl.b2 = bits - pl.b1;
+  const uint64_t mean1 = ceil_div(n, 1ull << pl.b1);
+  pl.cap1 = (uint32_t)((mean1 + mean1 * opt.bucket_slack_permille / 1000 + 1024 + 3) & ~3ull);
+  pl.usable = (n >> bits) <= pl.cap2 / 2 && n < (1ull << 29);
+  return pl;
+}
+
+int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl) {
+  cudaStream_t st = ctx.stream;
+  const uint64_t r1 = (uint64_t)pl.cap1 << pl.b1, r2 = (uint64_t)pl.cap2 << (pl.b1 + pl.b2);
+  STB_CUDA(ctx, ws.keys1.ensure(r1, st));
+  STB_CUDA(ctx, ws.pos1.ensure(r1, st));
+  STB_CUDA(ctx, ws.keys2.ensure(r2, st));
+  STB_CUDA(ctx, ws.pos2.ensure(r2, st));
+  STB_CUDA(ctx, ws.counters.ensure((1ull << pl.b1) + (1ull << (pl.b1 + pl.b2)) + 1, st));
+  // per device, and cheap: set on every call rather than remembered per process
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  return STB_OK;
+}
+
+int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
+                       const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out) {
+  cudaStream_t st = ctx.stream;
+  STB_TRY(bucket_reserve(ctx, ws, pl));
+  const uint32_t nb1 = 1u << pl.b1, nb = 1u << (pl.b1 + pl.b2);
+  uint32_t* count1 = ws.counters.ptr;
+  uint32_t* count2 = count1 + nb1;
+  uint32_t* overflow = count2 + nb;
+  STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 1) * 4, st));
+  {
+    Launch l(ctx, "bucket_partition");
+    partition_kernel<true><<<(unsigned)ceil_div(n_next, PT_TILE), PT_THREADS, PT_SMEM, st>>>(
+        cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits,
+        child_first, child_multi, overflow);
+  }
+  {
+    Launch l(ctx, "bucket_partition");
+    const dim3 grid((unsigned)ceil_div(pl.cap1, PT_TILE), nb1);
+    partition_kernel<false><<<grid, PT_THREADS, PT_SMEM, st>>>(nullptr, 0u, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr,
+                                                              ws.pos2.ptr, count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, overflow);
+  }
+  {
+    Launch l(ctx, "bucket_dedup");
+    bucket_dedup_kernel<<<nb, DD_THREADS, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, count2, pl.cap2, aux, first_bits, multi_bits, overflow);
+  }
+  *overflow_out = overflow;
+  return STB_OK;
+}
+
+}  // namespace stb

@@ -21,10 +21,12 @@
 //
 // IDs are first-occurrence ranks in position order, independent of which thread won
 // which atomic, so the result equals the reference's sequential emplace order.
+#include <cooperative_groups.h>
+
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 
+#include "bucket.cuh"
 #include "pack.cuh"
 #include "tree.h"
 
@@ -177,23 +179,6 @@ leaf_insert_u64_kernel(const unsigned long long* __restrict__ leaves, uint32_t n
   insert_leaf<DIRECT>(v, S, p, tab, tmp + p, flags);
 }
 
-// Singleton filter for the first node layer (its keys are pairs of leaf ids: no locality to
-// exploit, so every table access is a random HBM line).  Two bit planes that fit in L2: plane A
-// = "some position hashed here", plane B = "at least two did".  A position whose B bit stays
-// clear shares its filter cell with nobody, so its key occurs exactly once in the level: it is
-// a first occurrence that nobody will ever look up, and it skips the table altogether.
-struct SingletonFilter {
-  uint32_t* plane_a = nullptr;
-  uint32_t* plane_b = nullptr;
-  uint32_t log2_bits = 0;
-};
-
-__device__ __forceinline__ void filter_cell(const SingletonFilter& flt, unsigned long long key, uint32_t& word, uint32_t& bit) {
-  const uint32_t h = (uint32_t)mix64(key) >> (32 - flt.log2_bits);  // low half of the mix: the table uses the high half
-  word = h >> 5;
-  bit = 1u << (h & 31);
-}
-
 __device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p, uint32_t& l, uint32_t& r) {
   if (2 * (uint64_t)p + 1 < n_cur) {
     const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + p);
@@ -205,179 +190,77 @@ __device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, 
   }
 }
 
-__global__ void __launch_bounds__(LVL_THREADS)
-node_filter_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, SingletonFilter flt) {
-#pragma unroll
-  for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
-    if (p >= n_next) return;
-    uint32_t l, r, cl, cr, f, word, bit;
-    load_children(cur, n_cur, p, l, r);
-    canonical_node(l, r, cl, cr, f);
-    filter_cell(flt, ((unsigned long long)cl << 32) | cr, word, bit);
-    if (atomicOr(flt.plane_a + word, bit) & bit) atomicOr(flt.plane_b + word, bit);
-  }
+// Exact singleton filter (node levels above the first).  A node can only repeat an earlier node
+// if BOTH its children repeat: equal keys mean equal child ids, so the children of the later
+// node are later occurrences of the children of the earlier one, and the children of the earlier
+// one are first occurrences that occur again.  The child level left two bitmaps: `first` (its
+// first occurrences) and `multi` (first occurrences whose key occurred again).  A position with a
+// child that is a first occurrence and never occurred again holds the only node with that child:
+// it is a first occurrence that nobody will ever look up, and it skips the table altogether.
+// (A null right child counts as repeating: bits past the end of the child level are zero in `first`.)
+__device__ __forceinline__ bool children_both_repeat(const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
+                                                     uint32_t p) {
+  const uint32_t w = p >> 4, sh = (2u * p) & 31u;
+  const uint32_t repeats = ~__ldg(child_first + w) | __ldg(child_multi + w);
+  return ((repeats >> sh) & 3u) == 3u;
 }
 
-// One node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
-__global__ void __launch_bounds__(LVL_THREADS)
-node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ tmp,
-                   const uint32_t* __restrict__ child_unique, uint32_t serial, SingletonFilter flt, uint32_t first_block) {
-  // several positions per thread: CTAs that live for one probe each are dispatch-bound
-  for (int it = 0; it < LVL_ITERS; ++it) {
-  const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
-  if (p >= n_next) return;
-  uint32_t l, r;
+__device__ __forceinline__ uint32_t node_slot_start(const LevelTable& tab, uint32_t cl, uint32_t cr, uint32_t hashed,
+                                                    const uint32_t* __restrict__ child_unique, uint32_t& limit) {
+  limit = 0xffffffffu;
+  if (!child_unique) return hashed;
+  // Locality placement (node layers above the first): child ids are first-occurrence ranks, so
+  // they grow with the position; a slot proportional to a child id makes neighbouring positions
+  // probe neighbouring slots (one 128-byte line serves several positions instead of one line
+  // per position).  Crowded neighbourhoods (one child with many partners) fall back to the hash.
+  const uint32_t child = ptr_is_null(cl) ? (cr & IDX_MASK) : (cl & IDX_MASK);
+  // (any deterministic function of the key will do: single-precision scaling, no 64-bit divide)
+  const float ratio = __fdividef((float)tab.cap, (float)max(1u, __ldg(child_unique)));
+  limit = 24u;
+  // clamped in integers: (float)(cap - 9) rounds up for caps >= 2^25 and would let the probe
+  // start at or past `cap`, which tagged_insert only wraps at exactly
+  return min(tab.cap - 9u, (uint32_t)min(4.0e9f, (float)child * ratio)) + (hashed & 7u);
+}
+
+// One position of a node level: reduce_nodes + emplace_node (shared_tree.cpp:697-712, :662-672).
+// Returns true when the position skipped the table (certified singleton).
+__device__ __forceinline__ bool node_insert_position(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t p, const LevelTable& tab,
+                                                     uint32_t* __restrict__ aux, const uint32_t* __restrict__ child_unique, uint32_t serial,
+                                                     const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi) {
+  if (child_first && !children_both_repeat(child_first, child_multi, p)) return true;  // assign recomputes the node
+  uint32_t l, r, cl, cr, f, limit;
   load_children(cur, n_cur, p, l, r);
-  uint32_t cl, cr, f;
   canonical_node(l, r, cl, cr, f);
   const unsigned long long key = ((unsigned long long)cl << 32) | cr;
-  if (flt.plane_b) {
-    uint32_t word, bit;
-    filter_cell(flt, key, word, bit);
-    if (!(__ldcg(flt.plane_b + word) & bit)) {  // the only position with this key
-      atomicOr(tab.first_bits + (p >> 5), 1u << (p & 31));
-      continue;  // assign_kernel recomputes the node; nobody resolves through tmp[p]
-    }
-  }
   const uint32_t hashed = __umulhi(hash64(key), tab.cap);
-  uint32_t start = hashed, limit = 0xffffffffu;
-  if (child_unique) {
-    // Locality placement (node layers above the first): child ids are first-occurrence ranks, so
-    // they grow with the position; a slot proportional to a child id makes neighbouring positions
-    // probe neighbouring slots (one 128-byte line serves several positions instead of one line
-    // per position).  Crowded neighbourhoods (one child with many partners) fall back to the hash.
-    const uint32_t child = ptr_is_null(cl) ? (cr & IDX_MASK) : (cl & IDX_MASK);
-    // (any deterministic function of the key will do: single-precision scaling, no 64-bit divide)
-    const float ratio = __fdividef((float)tab.cap, (float)max(1u, __ldg(child_unique)));
-    start = (uint32_t)min((float)(tab.cap - 9u), (float)child * ratio) + (hashed & 7u);
-    limit = 24u;
-  }
-  tmp[p] = tagged_insert(tab.slots, tab.cap, key, p, serial, start, hashed, limit, tab.first_bits) | f;
-  }
+  const uint32_t start = node_slot_start(tab, cl, cr, hashed, child_unique, limit);
+  aux[p] = tagged_insert(tab.slots, tab.cap, key, p, serial, start, hashed, limit, tab.first_bits) | f;
+  return false;
 }
 
-// per-CTA first-occurrence counts (LVL_TILE positions = 32 bitmask words) for the scan
-__global__ void __launch_bounds__(256)
-bitmask_blockcnt_kernel(const uint32_t* __restrict__ bitmask, uint32_t n_blocks, uint32_t* __restrict__ blockcnt) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t blk = (blockIdx.x * 256 + threadIdx.x) >> 5;  // one warp per block of 1024 positions
-  if (blk >= n_blocks) return;
-  uint32_t c = __popc(bitmask[blk * (LVL_TILE / 32) + lane]);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-  if (lane == 0) blockcnt[blk] = c;
-}
-
-// In-place exclusive scan of the per-CTA counts (single CTA, 16 entries per thread and
-// round); total -> *total_out.
-constexpr int SCAN_PER_THREAD = 16;
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint32_t* __restrict__ cnt, uint32_t nb,
-                                                           uint32_t* total_out, const uint32_t* carry_in) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t carry_s;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = carry_in ? *carry_in : 0u;  // streaming build: ids continue where the last chunk stopped
-  __syncthreads();
-  for (uint32_t base = 0; base < nb; base += 1024 * SCAN_PER_THREAD) {
-    const uint32_t i0 = base + threadIdx.x * SCAN_PER_THREAD;
-    uint32_t v[SCAN_PER_THREAD];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; ++j) {
-      v[j] = i0 + j < nb ? cnt[i0 + j] : 0u;
-      sum += v[j];
-    }
-    uint32_t x = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sum[lane];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += y;
-      }
-      warp_sum[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    uint32_t run = carry_s + (warp ? warp_sum[warp - 1] : 0u) + x - sum;
-#pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; ++j) {
-      if (i0 + j < nb) cnt[i0 + j] = run;
-      run += v[j];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = run;
-    __syncthreads();
+__global__ void __launch_bounds__(LVL_THREADS)
+node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next, LevelTable tab, uint32_t* __restrict__ aux,
+                   const uint32_t* __restrict__ child_unique, uint32_t serial, const uint32_t* __restrict__ child_first,
+                   const uint32_t* __restrict__ child_multi, uint32_t first_block, const uint32_t* __restrict__ enable) {
+  if (enable && !*enable) return;  // the fallback of the on-chip path: runs only when a bucket overflowed
+  // several positions per thread: CTAs that live for one probe each are dispatch-bound
+#pragma unroll 1
+  for (int it = 0; it < LVL_ITERS; ++it) {
+    const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+    const bool skipped = p < n_next && node_insert_position(cur, n_cur, p, tab, aux, child_unique, serial, child_first, child_multi);
+    // a warp covers one word of the bitmap: certified singletons are marked with one atomic
+    const uint32_t word = __ballot_sync(0xffffffffu, skipped);
+    if ((threadIdx.x & 31) == 0 && word) atomicOr(tab.first_bits + (p >> 5), word);
   }
-  if (threadIdx.x == 0) *total_out = carry_s;
-}
-
-// Large levels: one CTA per chunk of 1024 * SCAN_PER_THREAD counts scans its chunk in place
-// (exclusive, from 0) and leaves the chunk total in chunk_sum[]; scan_blocks_kernel then scans
-// the few chunk totals, and assign_kernel adds its chunk's base.  The single-CTA loop over a
-// 3.1 Gbp leaf level is 16 dependent rounds; this is one.
-constexpr uint32_t SCAN_CHUNK = 1024 * SCAN_PER_THREAD;
-constexpr uint32_t SCAN_MAX_CHUNKS = 1024;
-__global__ void __launch_bounds__(1024) scan_chunks_kernel(uint32_t* __restrict__ cnt, uint32_t nb, uint32_t* __restrict__ chunk_sum) {
-  __shared__ uint32_t warp_sum[32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t i0 = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
-  uint32_t v[SCAN_PER_THREAD];
-  uint32_t sum = 0;
-#pragma unroll
-  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
-    v[j] = i0 + j < nb ? cnt[i0 + j] : 0u;
-    sum += v[j];
-  }
-  uint32_t x = sum;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-    if (lane >= d) x += y;
-  }
-  if (lane == 31) warp_sum[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = warp_sum[lane];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
-      if (lane >= d) w += y;
-    }
-    warp_sum[lane] = w;  // inclusive over warps
-  }
-  __syncthreads();
-  uint32_t run = (warp ? warp_sum[warp - 1] : 0u) + x - sum;
-#pragma unroll
-  for (int j = 0; j < SCAN_PER_THREAD; ++j) {
-    if (i0 + j < nb) cnt[i0 + j] = run;
-    run += v[j];
-  }
-  if (threadIdx.x == 1023) chunk_sum[blockIdx.x] = run;
 }
 
 enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
 
-// First occurrences: id = rank in position order; append the item to its layer in id order
-// and emit the finished pointer.  Node items are recomputed from the child pointers
-// (coalesced) rather than fetched from the table (random).
-template <int MODE>
-__global__ void __launch_bounds__(LVL_THREADS)
-assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
-              const uint32_t* __restrict__ blockbase, void* __restrict__ uniq, int S,
-              const uint32_t* __restrict__ children, uint32_t n_children, uint32_t first_block,
-              const uint32_t* __restrict__ chunk_base = nullptr) {
-  __shared__ uint32_t word_pref[32];
+// Loads the tile's 32 bitmap words (one per warp and iteration), leaves the exclusive prefix of
+// their popcounts in word_pref[0..31] and the tile's total in word_pref[32].
+__device__ __forceinline__ void tile_prefix(const uint32_t* __restrict__ bitmask, uint32_t block, uint32_t n, uint32_t (&words)[LVL_ITERS],
+                                            uint32_t* word_pref) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t block = first_block + blockIdx.x;
-  uint32_t words[LVL_ITERS];
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
     const uint32_t p0 = block * LVL_TILE + it * LVL_THREADS + warp * 32;
@@ -394,9 +277,19 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
       if (lane >= d) x += y;
     }
     word_pref[lane] = x - v;
+    if (lane == 31) word_pref[32] = x;
   }
   __syncthreads();
-  const uint32_t base = blockbase[block] + (chunk_base ? chunk_base[block / SCAN_CHUNK] : 0u);
+}
+
+// First occurrences of one tile: id = rank in position order; append the item to its layer in id
+// order and emit the finished pointer.  Node items are recomputed from the child pointers
+// (coalesced) rather than fetched from a table (random).
+template <int MODE>
+__device__ __forceinline__ void assign_tile(uint32_t block, uint32_t base, const uint32_t (&words)[LVL_ITERS], const uint32_t* word_pref,
+                                            uint32_t* __restrict__ tmp, uint32_t n, const LevelTable& tab, void* __restrict__ uniq, int S,
+                                            const uint32_t* __restrict__ children, uint32_t n_children) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
     const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
@@ -411,16 +304,8 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
       } else if (MODE == MODE_LEAF_HASH) {
         reinterpret_cast<unsigned long long*>(uniq)[rank] = (s == tab.cap) ? EMPTY_KEY : __ldcg(&tab.slots[s].key);
       } else {
-        uint32_t l, r;
-        if (2 * (uint64_t)p + 1 < n_children) {
-          const uint2 pr = __ldg(reinterpret_cast<const uint2*>(children) + p);
-          l = pr.x;
-          r = pr.y;
-        } else {
-          l = children[2 * (uint64_t)p];
-          r = PTR_NULL;
-        }
-        uint32_t cl, cr;
+        uint32_t l, r, cl, cr;
+        load_children(children, n_children, p, l, r);
         canonical_node(l, r, cl, cr, flags);
         reinterpret_cast<uint2*>(uniq)[rank] = make_uint2(cl, cr);
       }
@@ -429,124 +314,117 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
   }
 }
 
-// Later occurrences: direct mode looks the id up in the (L2-sized) id table; hash levels
-// read it from the finished pointer of the first occurrence, whose position count_first
-// left in tmp[p].
-template <bool DIRECT>
+// Tile states of the single-pass scan (decoupled look-back): one 64-bit word per tile,
+// (flag << 32) | value; flag 0 = nothing yet, 1 = the tile's own count, 2 = the inclusive prefix.
+// scan[0] is the ticket counter that hands out tiles in launch order, scan[1 + tile] the state.
+constexpr unsigned long long SCAN_AGGREGATE = 1ull << 32, SCAN_INCLUSIVE = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long scan_state_load(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void scan_state_store(unsigned long long* p, unsigned long long v) {
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+// ids of one level in ONE pass: every CTA takes the next tile (ticket), publishes the number of
+// first occurrences in it, looks back over its predecessors' states for its base and assigns.
+// The ids are ranks in position order whatever the order the tiles finish in.  A tile only ever
+// waits for tiles with smaller tickets, which are running or done, so the look-back cannot stall.
+// The streaming build continues a level chunk after chunk: its states persist and the first tile
+// of a chunk finds the inclusive prefix the previous chunk left.
+template <int MODE>
 __global__ void __launch_bounds__(LVL_THREADS)
-resolve_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask, uint32_t first_block) {
+assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask, unsigned long long* __restrict__ scan,
+              uint32_t last_block, uint32_t* __restrict__ total_out, void* __restrict__ uniq, int S, const uint32_t* __restrict__ children,
+              uint32_t n_children) {
+  __shared__ uint32_t word_pref[33];
+  __shared__ uint32_t s_block, s_base;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_block = (uint32_t)atomicAdd(scan, 1ull);
+  __syncthreads();
+  const uint32_t block = s_block;
+  unsigned long long* state = scan + 1;
+  uint32_t words[LVL_ITERS];
+  tile_prefix(bitmask, block, n, words, word_pref);
+  if (warp == 0) {
+    const uint32_t total = word_pref[32];
+    if (lane == 0 && block > 0) scan_state_store(state + block, SCAN_AGGREGATE | total);
+    uint32_t base = 0;
+    for (int64_t at = (int64_t)block - 1 - lane;; at -= 32) {
+      // the tile before the first one has the inclusive prefix 0
+      unsigned long long st = at >= 0 ? scan_state_load(state + at) : SCAN_INCLUSIVE;
+      while (__any_sync(0xffffffffu, (st >> 32) == 0)) {
+        if ((st >> 32) == 0) st = scan_state_load(state + at);
+      }
+      const uint32_t inclusive = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+      const uint32_t upto = inclusive ? (uint32_t)__ffs(inclusive) - 1u : 31u;  // nearest tile that already knows its prefix
+      uint32_t v = lane <= upto ? (uint32_t)st : 0u;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      base += v;
+      if (inclusive) break;
+    }
+    if (lane == 0) {
+      scan_state_store(state + block, SCAN_INCLUSIVE | (base + total));
+      s_base = base;
+      if (block == last_block) *total_out = base + total;
+    }
+  }
+  __syncthreads();
+  assign_tile<MODE>(block, s_base, words, word_pref, tmp, n, tab, uniq, S, children, n_children);
+}
+
+// Later occurrences.  RESOLVE_DIRECT (ACGT leaves): the id is in the (L2-sized) id table.
+// Otherwise the id is read from the finished pointer of the first occurrence, whose position is
+// either in the slot aux[p] names (hash-table levels) or in aux[p] itself (levels deduplicated on
+// chip, bucket.cu: `firstpos_unless` points at their overflow flag).  Hash-table levels also mark
+// the first occurrence in `multi_bits`: its key occurred again (children_both_repeat reads it).
+enum { RESOLVE_DIRECT = 0, RESOLVE_TABLE = 1 };
+template <int MODE>
+__global__ void __launch_bounds__(LVL_THREADS)
+resolve_kernel(const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
+               uint32_t first_block, uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ firstpos_unless) {
   const uint32_t lane = threadIdx.x & 31;
+  const bool firstpos = firstpos_unless && *firstpos_unless == 0u;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
     const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
     if (p < n) {
       const uint32_t word = bitmask[p >> 5];
       if (!((word >> lane) & 1u)) {
-        const uint32_t t = tmp[p];
+        const uint32_t t = aux[p];
         const uint32_t s = t & IDX_MASK;
-        // hash levels: slot -> position of the first occurrence -> its finished pointer -> id
-        const uint32_t id = DIRECT ? __ldcg(tab.dids + s) : (__ldcg(tmp + __ldcg(&tab.slots[s].minpos)) & IDX_MASK);
-        tmp[p] = finish_pointer(id, t & ~IDX_MASK);
+        uint32_t id;
+        if (MODE == RESOLVE_DIRECT) {
+          id = __ldcg(tab.dids + s);
+        } else {
+          uint32_t q = s;
+          if (!firstpos) {
+            q = __ldcg(&tab.slots[s].minpos);
+            if (multi_bits) atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
+          }
+          id = __ldcg(out + q) & IDX_MASK;
+        }
+        out[p] = finish_pointer(id, t & ~IDX_MASK);
       }
     }
   }
 }
 
-// ---- host orchestration -----------------------------------------------------------
-
-namespace {
-
-struct LeafInput {
-  const char* body = nullptr;                 // device, 16-byte aligned
-  const unsigned long long* leaves = nullptr; // device
-};
-
-struct Scratch {
-  DevBuf<uint32_t> ptr_a, ptr_b, bitmask, blockcnt, chunk_sum, counts, dminpos, dids;
-  DevBuf<Slot> slots;
-  DevBuf<BuildFlags> flags;
-  DevBuf<uint32_t> root;
-  // Node tables: a slot's last word is an epoch tag; every node level of every build on this
-  // handle takes a fresh serial, so the table is cleared only when its memory is new.
-  bool tags_cleared = false;
-  uint32_t serial = 0;
-  DevBuf<uint32_t> filter;    // singleton filter of the first node layer (two bit planes)
-
-  // streaming build (host input): every chunked level keeps its own pointer array, bitmap,
-  // per-CTA counts and table for the whole build
-  DevBuf<uint32_t> ptr_arena, bit_arena, cnt_arena, level_sizes;
-  DevBuf<Slot> stream_slots;
-  cudaStream_t copy_stream = nullptr;
-  std::vector<cudaEvent_t> chunk_events;
-  ~Scratch() {
-    for (auto e : chunk_events) cudaEventDestroy(e);
-    if (copy_stream) cudaStreamDestroy(copy_stream);
-  }
-};
-
-Scratch& workspace_of(Tree& t) {
-  if (!t.workspace) t.workspace = std::make_shared<Scratch>();
-  Scratch& sc = *static_cast<Scratch*>(t.workspace.get());
-  if (sc.serial > 0xfff00000u) {  // far from wrapping into a tag that is still in the table
-    sc.serial = 0;
-    sc.tags_cleared = false;
-  }
-  return sc;
-}
-
-uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
-
-template <int S_T, bool DIRECT>
-void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags, uint32_t pos0 = 0) {
-  const size_t smem = pack_smem_bytes(ctx.S);
-  Launch l(ctx, "leaf_insert");
-  if (S_T == 12 && DIRECT) {
-    leaf_insert_acgt12_kernel<<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(body, n, tab, tmp, flags, pos0);
-    return;
-  }
-  leaf_insert_text_kernel<S_T, DIRECT><<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(
-      body, n, ctx.S, tab, tmp, flags, pos0);
-}
-
-// count -> scan -> assign -> resolve for one level whose inserts are already queued.
-template <int MODE>
-void finish_level(Ctx& ctx, uint32_t* tmp, uint32_t n, LevelTable tab, Scratch& sc, uint32_t* total_out, void* uniq,
-                  const uint32_t* children = nullptr, uint32_t n_children = 0) {
-  constexpr bool DIRECT = (MODE == MODE_LEAF_DIRECT);
-  const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
-  {  // the inserts kept the first-occurrence bitmap current: count it per CTA tile for the scan
-    Launch l(ctx, "bitmask_blockcnt");
-    bitmask_blockcnt_kernel<<<(unsigned)ceil_div((uint64_t)nb * 32, 256), 256, 0, ctx.stream>>>(sc.bitmask.ptr, nb, sc.blockcnt.ptr);
-  }
-  const uint32_t* chunk_base = nullptr;
-  if (nb > SCAN_CHUNK && sc.chunk_sum.ptr) {  // two levels: chunks in parallel, then their (few) totals
-    const unsigned nchunks = (unsigned)ceil_div(nb, SCAN_CHUNK);
-    {
-      Launch l(ctx, "scan_blocks");
-      scan_chunks_kernel<<<nchunks, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, sc.chunk_sum.ptr);
-    }
-    Launch l(ctx, "scan_blocks");
-    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.chunk_sum.ptr, nchunks, total_out, nullptr);
-    chunk_base = sc.chunk_sum.ptr;
-  } else {
-    Launch l(ctx, "scan_blocks");
-    scan_blocks_kernel<<<1, 1024, 0, ctx.stream>>>(sc.blockcnt.ptr, nb, total_out, nullptr);
-  }
-  {
-    Launch l(ctx, "assign_ids");
-    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, sc.blockcnt.ptr, uniq, ctx.S, children, n_children, 0u,
-                                                            chunk_base);
-  }
-  {
-    Launch l(ctx, "resolve_ids");
-    resolve_kernel<DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(tmp, n, tab, sc.bitmask.ptr, 0u);
+// Clears the level's bitmaps when the on-chip path gave up (the hash-table fallback starts from zero).
+__global__ void __launch_bounds__(256) bitmaps_reset_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b, uint32_t words,
+                                                            const uint32_t* __restrict__ enable) {
+  if (!*enable) return;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < words; i += gridDim.x * 256) {
+    a[i] = 0u;
+    b[i] = 0u;
   }
 }
 
 // ---- the small top of the tree in ONE launch ----------------------------------------------
 // Once a level has at most SMALL_MAX pointers, every remaining level (about a dozen) runs inside
 // a single CTA: pointers ping-pong in shared memory, the hash table lives in shared memory, and
-// __syncthreads() replaces the ~5 launches per level of the general path.
+// __syncthreads() replaces the launches per level of the general path.
 constexpr uint32_t SMALL_MAX = 2048;        // pointers entering the kernel (<= 1024 positions per level)
 constexpr uint32_t SMALL_SLOTS = 2048;      // shared-memory table slots (load <= 0.5)
 constexpr int SMALL_MAX_LEVELS = 16;
@@ -622,28 +500,242 @@ small_levels_kernel(const uint32_t* __restrict__ cur_in, uint32_t n_cur, SmallOu
   if (tid == 0) *root_out = cur[0];
 }
 
-// Tunables of the partitioned path (environment overrides are for experiments only).
-static uint64_t env_u64(const char* name, uint64_t fallback) {
-  const char* v = getenv(name);
-  return v ? strtoull(v, nullptr, 0) : fallback;
+// ---- the middle of the tree in ONE cooperative launch -------------------------------------
+// Levels between the small top (above) and the large bottom are launch-bound when every phase is
+// its own kernel: a level of half a million positions is a few microseconds of work per phase.
+// Here a grid that fits the machine walks them all; grid.sync() stands where the kernel
+// boundaries were.  Tables, bitmaps and the exact singleton filter are those of the large levels.
+constexpr int MID_MAX_LEVELS = 24;
+
+struct MidLevels {
+  int levels;                     // levels this launch builds
+  uint2* nodes[MID_MAX_LEVELS];   // their layer buffers
+};
+
+__global__ void __launch_bounds__(LVL_THREADS)
+mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels out, Slot* slots, uint32_t serial0, uint32_t* aux,
+                  uint32_t* bits0, uint32_t* bits1, uint32_t* multi0, uint32_t* multi1, uint32_t parity, bool first_is_upper,
+                  bool use_filter, bool locality, uint32_t* blockcnt, uint32_t* counts) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t word_pref[33];
+  __shared__ uint32_t warp_red[LVL_THREADS / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* cur = buf_a;
+  uint32_t* nxt = buf_b;
+  for (int lv = 0; lv < out.levels; ++lv) {
+    const uint32_t n_next = (n_cur + 1) / 2;
+    const uint32_t nb = (n_next + LVL_TILE - 1) / LVL_TILE;
+    const uint32_t par = (parity + lv) & 1u;
+    uint32_t* first_bits = par ? bits1 : bits0;
+    uint32_t* multi_bits = par ? multi1 : multi0;
+    const uint32_t* child_first = par ? bits0 : bits1;
+    const uint32_t* child_multi = par ? multi0 : multi1;
+    // the first level of a call pairs leaf ids (or an imported array): no child bitmaps, no child count
+    const bool upper = first_is_upper || lv > 0;
+    const bool filter = use_filter && upper;
+    LevelTable tab{slots, nullptr, nullptr, (uint32_t)min((unsigned long long)max(1024u, 2u * n_next), 0x1ffffffeull)};
+    tab.first_bits = first_bits;
+    const uint32_t* child_unique = (locality && upper) ? counts + lv - 1 : nullptr;
+    // insert
+    for (uint32_t block = blockIdx.x; block < nb; block += gridDim.x) {
+#pragma unroll 1
+      for (int it = 0; it < LVL_ITERS; ++it) {
+        const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+        const bool skipped = p < n_next && node_insert_position(cur, n_cur, p, tab, aux, child_unique, serial0 + lv,
+                                                                filter ? child_first : nullptr, child_multi);
+        const uint32_t word = __ballot_sync(0xffffffffu, skipped);
+        if (lane == 0 && word) atomicOr(first_bits + (p >> 5), word);
+      }
+    }
+    grid.sync();
+    // first occurrences per tile; the bitmaps of the level after this one (the child bitmaps of
+    // this level, no longer needed) are cleared on the way
+    for (uint32_t t = blockIdx.x * (LVL_THREADS / 32) + warp; t < nb; t += gridDim.x * (LVL_THREADS / 32)) {
+      uint32_t c = __popc(first_bits[t * (LVL_TILE / 32) + lane]);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (lane == 0) blockcnt[t] = c;
+    }
+    {
+      const uint32_t words_after = (((n_next + 1) / 2 + LVL_TILE - 1) / LVL_TILE) * (LVL_TILE / 32);
+      uint32_t* za = par ? bits0 : bits1;
+      uint32_t* zb = par ? multi0 : multi1;
+      for (uint32_t i = blockIdx.x * LVL_THREADS + threadIdx.x; i < words_after; i += gridDim.x * LVL_THREADS) {
+        za[i] = 0u;
+        zb[i] = 0u;
+      }
+    }
+    grid.sync();
+    // assign: a tile's base is the sum of the counts before it (at most a few thousand: every CTA adds them up itself)
+    for (uint32_t block = blockIdx.x; block < nb; block += gridDim.x) {
+      uint32_t part = 0;
+      for (uint32_t i = threadIdx.x; i < block; i += LVL_THREADS) part += blockcnt[i];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+      __syncthreads();  // word_pref / warp_red of the previous tile are no longer read
+      if (lane == 0) warp_red[warp] = part;
+      uint32_t words[LVL_ITERS];
+      tile_prefix(first_bits, block, n_next, words, word_pref);
+      uint32_t base = 0;
+#pragma unroll
+      for (int w = 0; w < LVL_THREADS / 32; ++w) base += warp_red[w];
+      if (block == nb - 1 && threadIdx.x == 0) counts[lv] = base + word_pref[32];
+      assign_tile<MODE_NODE>(block, base, words, word_pref, nxt, n_next, tab, out.nodes[lv], 0, cur, n_cur);
+    }
+    grid.sync();
+    // resolve
+    for (uint32_t block = blockIdx.x; block < nb; block += gridDim.x) {
+#pragma unroll
+      for (int it = 0; it < LVL_ITERS; ++it) {
+        const uint32_t p = block * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+        if (p < n_next && !((first_bits[p >> 5] >> lane) & 1u)) {
+          const uint32_t t = aux[p];
+          const uint32_t q = __ldcg(&tab.slots[t & IDX_MASK].minpos);
+          atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
+          nxt[p] = finish_pointer(__ldcg(nxt + q) & IDX_MASK, t & ~IDX_MASK);
+        }
+      }
+    }
+    grid.sync();
+    uint32_t* sw = cur;
+    cur = nxt;
+    nxt = sw;
+    n_cur = n_next;
+  }
 }
 
-// words of the two filter planes for a first node layer of n positions (0 = filter not used)
-static uint64_t filter_words(uint64_t n) {
-  if (n < env_u64("STB_FILTER_MIN", 1ull << 22)) return 0;
-  uint32_t log2_bits = 22;
-  while (log2_bits < 28 && (1ull << log2_bits) < 2 * n) ++log2_bits;
-  return 2 * ((1ull << log2_bits) / 32);
+// ---- host orchestration -----------------------------------------------------------
+
+namespace {
+
+struct LeafInput {
+  const char* body = nullptr;                 // device, 16-byte aligned
+  const unsigned long long* leaves = nullptr; // device
+};
+
+struct Scratch {
+  DevBuf<uint32_t> ptr_a, ptr_b, aux, bitmask, counts, dminpos, dids, blockcnt;
+  DevBuf<uint32_t> lvl_bits[2], lvl_multi[2];  // node levels: first occurrences / first occurrences that occur again, by level parity
+  DevBuf<unsigned long long> scan;             // ticket + tile states of the single-pass id scan
+  DevBuf<Slot> slots;
+  DevBuf<BuildFlags> flags;
+  DevBuf<uint32_t> root;
+  BucketWorkspace bucket;
+  // Node tables: a slot's last word is an epoch tag; every node level of every build on this
+  // handle takes a fresh serial, so the table is cleared only when its memory is new.
+  bool tags_cleared = false;
+  uint32_t serial = 0;
+  // the streaming build's per-level tables (stream_slots) count their own epochs: a reset of one
+  // counter must never make a tag that is still stored in the other table current again
+  bool stream_tags_cleared = false;
+  uint32_t stream_serial = 0;
+
+  // streaming build (host input): every chunked level keeps its own pointer array, bitmap,
+  // scan states and table for the whole build
+  DevBuf<uint32_t> ptr_arena, bit_arena, level_sizes;
+  DevBuf<unsigned long long> scan_arena;
+  DevBuf<Slot> stream_slots;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_events;
+  int coop_grid = 0;  // CTAs of the cooperative middle launch (0 = not yet asked)
+  ~Scratch() {
+    for (auto e : chunk_events) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  }
+};
+
+Scratch& workspace_of(Tree& t) {
+  if (!t.workspace) t.workspace = std::make_shared<Scratch>();
+  Scratch& sc = *static_cast<Scratch*>(t.workspace.get());
+  if (sc.serial > 0xfff00000u) {  // far from wrapping into a tag that is still in the table
+    sc.serial = 0;
+    sc.tags_cleared = false;
+  }
+  if (sc.stream_serial > 0xfff00000u) {
+    sc.stream_serial = 0;
+    sc.stream_tags_cleared = false;
+  }
+  return sc;
+}
+
+uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
+uint64_t bitmap_words(uint64_t n) { return ceil_div(n, LVL_TILE) * (LVL_TILE / 32); }
+
+template <int S_T, bool DIRECT>
+void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, uint32_t* tmp, BuildFlags* flags, uint32_t pos0 = 0) {
+  const size_t smem = pack_smem_bytes(ctx.S);
+  Launch l(ctx, "leaf_insert");
+  if (S_T == 12 && DIRECT) {
+    leaf_insert_acgt12_kernel<<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(body, n, tab, tmp, flags, pos0);
+    return;
+  }
+  leaf_insert_text_kernel<S_T, DIRECT><<<(unsigned)ceil_div(n, PACK_TILE_LEAVES), PACK_THREADS, smem, ctx.stream>>>(
+      body, n, ctx.S, tab, tmp, flags, pos0);
+}
+
+// assign -> resolve for one level whose inserts are already queued.  `aux` is what the inserts
+// left per position, `out` receives the finished pointers (the same array for the leaf level).
+template <int MODE>
+int finish_level(Ctx& ctx, const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, const uint32_t* bitmask, unsigned long long* scan,
+                 uint32_t* total_out, void* uniq, const uint32_t* children = nullptr, uint32_t n_children = 0, uint32_t* multi_bits = nullptr,
+                 const uint32_t* firstpos_unless = nullptr) {
+  const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
+  STB_CUDA(ctx, cudaMemsetAsync(scan, 0, ((uint64_t)nb + 1) * 8, ctx.stream));
+  {
+    Launch l(ctx, "assign_ids");
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(out, n, tab, bitmask, scan, nb - 1, total_out, uniq, ctx.S, children, n_children);
+  }
+  {
+    Launch l(ctx, "resolve_ids");
+    if (MODE == MODE_LEAF_DIRECT) resolve_kernel<RESOLVE_DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(aux, out, n, tab, bitmask, 0u, nullptr, nullptr);
+    else resolve_kernel<RESOLVE_TABLE><<<nb, LVL_THREADS, 0, ctx.stream>>>(aux, out, n, tab, bitmask, 0u, multi_bits, firstpos_unless);
+  }
+  return STB_OK;
+}
+
+// Everything run_node_levels needs for a pointer array of n_cur entries.
+int reserve_node_workspace(Tree& t, Scratch& sc, uint64_t n_cur) {
+  cudaStream_t st = t.stream;
+  const uint64_t n1 = ceil_div(n_cur, 2), n2 = ceil_div(n1, 2);
+  STB_CUDA(t, sc.ptr_a.ensure(n_cur, st));
+  STB_CUDA(t, sc.ptr_b.ensure(n1, st));
+  STB_CUDA(t, sc.aux.ensure(n1, st));
+  STB_CUDA(t, sc.lvl_bits[0].ensure(bitmap_words(n1), st));
+  STB_CUDA(t, sc.lvl_multi[0].ensure(bitmap_words(n1), st));
+  STB_CUDA(t, sc.lvl_bits[1].ensure(bitmap_words(n2), st));
+  STB_CUDA(t, sc.lvl_multi[1].ensure(bitmap_words(n2), st));
+  STB_CUDA(t, sc.scan.ensure(ceil_div(n_cur, LVL_TILE) + 2, st));
+  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(std::min<uint64_t>(n1, std::max<uint64_t>(t.opt.coop_max, SMALL_MAX)), LVL_TILE) + 1, st));
+  STB_CUDA(t, sc.counts.ensure(80, st));
+  STB_CUDA(t, sc.root.ensure(1, st));
+  {
+    bool grew = false;
+    STB_CUDA(t, sc.slots.ensure((uint64_t)table_cap(n1) + 1, st, &grew));
+    if (grew) sc.tags_cleared = false;
+  }
+  if (n1 >= t.opt.bucket_min && t.opt.bucket_levels > 0) {
+    const BucketPlan pl = bucket_plan(n1, t.opt);  // the largest level: later ones fit in what it reserves
+    if (pl.usable) STB_TRY(bucket_reserve(t, sc.bucket, pl));
+  }
+  return STB_OK;
 }
 
 // Node levels from a pointer array down to a single root pointer.  Appends one layer per
 // level to t.layers; counts_dev[level] receives each layer's size; returns the buffer that
-// holds the root pointer in *root_buf.
+// holds the root pointer in *root_buf.  The workspace must have been reserved for n_cur.
 int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t n_cur, uint32_t* counts_dev, int* levels_out,
                     uint32_t** root_buf) {
-  static const bool locality = env_u64("STB_LOCALITY", 1) != 0;
   cudaStream_t st = t.stream;
   int level = 0;
+  if (!sc.tags_cleared) {
+    // Node tables are never cleared between levels: a slot's last word is an epoch tag and a
+    // slot whose tag is not this level's serial counts as empty.  One clear per allocation.
+    Launch l(t, "table_clear", false);
+    STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, sc.slots.bytes(), st));
+    sc.tags_cleared = true;
+    sc.serial = 0;
+  }
   do {
     if (n_cur <= SMALL_MAX) {  // the rest of the tree in one launch
       SmallOut out{};
@@ -655,53 +747,82 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
         out.nodes[extra++] = t.layers.back().nodes.ptr;
         if (n <= 1) break;
       }
-      STB_CUDA(t, sc.root.ensure(1, st));
       Launch l(t, "small_levels");
       small_levels_kernel<<<1, 1024, 0, st>>>(cur, (uint32_t)n_cur, out, counts_dev + level, sc.root.ptr);
       level += extra;
       cur = sc.root.ptr;
       break;
     }
+    const uint32_t par = (uint32_t)level & 1u;
     const uint64_t n_next = ceil_div(n_cur, 2);
+    const BucketPlan pl = (n_next >= t.opt.bucket_min && (uint64_t)level < t.opt.bucket_levels) ? bucket_plan(n_next, t.opt) : BucketPlan{};
+    if (!pl.usable && n_cur <= t.opt.coop_max) {  // the middle of the tree in one cooperative launch
+      if (sc.coop_grid == 0) {
+        int per_sm = 0, sms = 0;
+        STB_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mid_levels_kernel, LVL_THREADS, 0));
+        STB_CUDA(t, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t.device));
+        sc.coop_grid = std::max(1, std::min(per_sm, 4) * sms);
+      }
+      MidLevels out{};
+      uint64_t n = n_cur;
+      while (n > SMALL_MAX && out.levels < MID_MAX_LEVELS) {
+        n = ceil_div(n, 2);
+        t.layers.emplace_back();
+        STB_CUDA(t, t.layers.back().nodes.alloc(n, st));
+        out.nodes[out.levels++] = t.layers.back().nodes.ptr;
+      }
+      const uint64_t n_first = ceil_div(n_cur, 2);
+      STB_CUDA(t, cudaMemsetAsync(sc.lvl_bits[par].ptr, 0, bitmap_words(n_first) * 4, st));
+      STB_CUDA(t, cudaMemsetAsync(sc.lvl_multi[par].ptr, 0, bitmap_words(n_first) * 4, st));
+      uint32_t n_cur32 = (uint32_t)n_cur, serial0 = sc.serial + 1, parity = par;
+      sc.serial += (uint32_t)out.levels;
+      bool first_is_upper = level > 0, use_filter = t.opt.child_filter != 0, locality = t.opt.locality != 0;
+      Slot* slots = sc.slots.ptr;
+      uint32_t *aux = sc.aux.ptr, *b0 = sc.lvl_bits[0].ptr, *b1 = sc.lvl_bits[1].ptr, *m0 = sc.lvl_multi[0].ptr, *m1 = sc.lvl_multi[1].ptr;
+      uint32_t *blockcnt = sc.blockcnt.ptr, *counts = counts_dev + level;
+      void* args[] = {&cur, &nxt, &n_cur32, &out, &slots, &serial0, &aux, &b0, &b1, &m0, &m1, &parity, &first_is_upper, &use_filter, &locality, &blockcnt, &counts};
+      const unsigned grid = (unsigned)std::min<uint64_t>(sc.coop_grid, ceil_div(n_first, LVL_TILE));
+      Launch l(t, "mid_levels");
+      STB_CUDA(t, cudaLaunchCooperativeKernel((const void*)mid_levels_kernel, dim3(grid), dim3(LVL_THREADS), args, 0, st));
+      if (out.levels & 1) std::swap(cur, nxt);
+      n_cur = n;
+      level += out.levels;
+      continue;
+    }
     t.layers.emplace_back();
     Layer& layer = t.layers.back();
     STB_CUDA(t, layer.nodes.alloc(n_next, st));
+    uint32_t* first_bits = sc.lvl_bits[par].ptr;
+    uint32_t* multi_bits = sc.lvl_multi[par].ptr;
     LevelTable nt{sc.slots.ptr, nullptr, nullptr, table_cap(n_next)};
-    nt.first_bits = sc.bitmask.ptr;
-    if (!sc.tags_cleared) {
-      // Node tables are never cleared between levels: a slot's last word is an epoch tag and a
-      // slot whose tag is not this level's serial counts as empty.  One clear per build.
-      Launch l(t, "table_clear", false);
-      STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, sc.slots.bytes(), st));
-      sc.tags_cleared = true;
-      sc.serial = 0;
-    }
-    STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n_next, LVL_TILE) * (LVL_TILE / 8), st));
-    SingletonFilter flt;
-    static const uint64_t filter_min = env_u64("STB_FILTER_MIN", 1ull << 22);
-    if (level == 0 && n_next >= filter_min) {
-      // two planes of 2^k bits, k as large as keeps both in L2 (<= 2 x 32 MiB)
-      static const uint32_t max_log2 = (uint32_t)env_u64("STB_FILTER_LOG2", 28);
-      flt.log2_bits = 22;
-      while (flt.log2_bits < max_log2 && (1ull << flt.log2_bits) < 2 * n_next) ++flt.log2_bits;
-      const uint64_t words = (1ull << flt.log2_bits) / 32;
-      STB_CUDA(t, sc.filter.ensure(2 * words, st));  // already there: sized with the rest of the workspace
-      STB_CUDA(t, cudaMemsetAsync(sc.filter.ptr, 0, 2 * words * 4, st));
-      flt.plane_a = sc.filter.ptr;
-      flt.plane_b = sc.filter.ptr + words;
-      Launch l(t, "node_filter");
-      node_filter_kernel<<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, flt);
+    nt.first_bits = first_bits;
+    STB_CUDA(t, cudaMemsetAsync(first_bits, 0, bitmap_words(n_next) * 4, st));
+    STB_CUDA(t, cudaMemsetAsync(multi_bits, 0, bitmap_words(n_next) * 4, st));
+    // the exact singleton filter reads the bitmaps the level below left (not below the first level:
+    // its children are leaf ids or an imported array, whose bitmaps this call has not built)
+    const bool filter = level > 0 && t.opt.child_filter != 0;
+    const uint32_t* child_first = filter ? sc.lvl_bits[par ^ 1u].ptr : nullptr;
+    const uint32_t* child_multi = filter ? sc.lvl_multi[par ^ 1u].ptr : nullptr;
+    // children of level 0 are leaf ids (or an imported array): not position-ordered
+    const uint32_t* child_unique = (t.opt.locality && level > 0) ? counts_dev + level - 1 : nullptr;
+    const unsigned nb = (unsigned)ceil_div(n_next, LVL_TILE);
+    uint32_t* overflow = nullptr;
+    if (pl.usable) {
+      // on chip (bucket.cu); the hash-table kernels below then run only if a bucket overflowed
+      STB_TRY(bucket_dedup_level(t, sc.bucket, pl, cur, (uint32_t)n_cur, (uint32_t)n_next, child_first, child_multi, sc.aux.ptr, first_bits, multi_bits,
+                                 &overflow));
+      Launch l(t, "bucket_fallback");
+      bitmaps_reset_kernel<<<296, 256, 0, st>>>(first_bits, multi_bits, (uint32_t)bitmap_words(n_next), overflow);
     }
     {
       // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
       // and chunking the level to keep table lines in L2 did not pay (profiles/README.md).
-      Launch l(t, "node_insert");
-      // children of level 0 are leaf ids (or an imported array): not position-ordered
-      const uint32_t* child_unique = (locality && level > 0) ? counts_dev + level - 1 : nullptr;
-      node_insert_kernel<<<(unsigned)ceil_div(n_next, LVL_TILE), LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, nxt, child_unique,
-                                                                                          ++sc.serial, flt, 0u);
+      Launch l(t, pl.usable ? "bucket_fallback" : "node_insert");
+      node_insert_kernel<<<nb, LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, sc.aux.ptr, child_unique, ++sc.serial, child_first,
+                                                      child_multi, 0u, overflow);
     }
-    finish_level<MODE_NODE>(t, nxt, (uint32_t)n_next, nt, sc, counts_dev + level, layer.nodes.ptr, cur, (uint32_t)n_cur);
+    STB_TRY(finish_level<MODE_NODE>(t, sc.aux.ptr, nxt, (uint32_t)n_next, nt, first_bits, sc.scan.ptr, counts_dev + level, layer.nodes.ptr, cur,
+                                    (uint32_t)n_cur, multi_bits, overflow));
     std::swap(cur, nxt);
     n_cur = n_next;
     ++level;
@@ -770,16 +891,9 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   const int S = t.S;
   cudaStream_t st = t.stream;
   Scratch& sc = workspace_of(t);
-  const uint64_t n1 = ceil_div(n0, 2);
-  STB_CUDA(t, sc.ptr_a.ensure(n0, st));
-  STB_CUDA(t, sc.ptr_b.ensure(n1, st));
-  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n0, LVL_TILE) * (LVL_TILE / 32), st));
-  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n0, LVL_TILE) + 1, st));
-  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
-  STB_CUDA(t, sc.counts.ensure(80, st));
+  STB_TRY(reserve_node_workspace(t, sc, n0));
+  STB_CUDA(t, sc.bitmask.ensure(bitmap_words(n0), st));
   STB_CUDA(t, sc.flags.ensure(1, st));
-  STB_CUDA(t, sc.root.ensure(1, st));
-  STB_CUDA(t, sc.filter.ensure(filter_words(n1), st));
   {
     BuildFlags init{~0ull, 0u, 0u};
     STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -788,15 +902,16 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   // ---- leaf level ----
   const uint64_t direct_entries = direct ? (1ull << (2 * S)) : 0;
   const uint32_t leaf_cap = direct ? 0u : table_cap(n0);
-  const uint32_t node_cap_max = table_cap(n1);
-  {
+  if (!direct) {
     bool grew = false;
-    STB_CUDA(t, sc.slots.ensure((uint64_t)std::max(leaf_cap, node_cap_max) + 1, st, &grew));
+    // the hashed leaf level uses the node table untagged: what it leaves there carries the tag
+    // 0xffffffff, which is never a level's serial, so the node levels see those slots as empty
+    STB_CUDA(t, sc.slots.ensure((uint64_t)leaf_cap + 1, st, &grew));
     if (grew) sc.tags_cleared = false;
   }
   LevelTable tab{sc.slots.ptr, nullptr, nullptr, leaf_cap};
   tab.first_bits = sc.bitmask.ptr;
-  STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, ceil_div(n0, LVL_TILE) * (LVL_TILE / 8), st));
+  STB_CUDA(t, cudaMemsetAsync(sc.bitmask.ptr, 0, bitmap_words(n0) * 4, st));
   if (direct) {
     STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
     STB_CUDA(t, sc.dids.ensure(direct_entries, st));
@@ -825,8 +940,8 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
     if (direct) leaf_insert_u64_kernel<true><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
     else leaf_insert_u64_kernel<false><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
   }
-  if (direct) finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, (uint32_t)n0, tab, sc, sc.counts.ptr, t.leaves.ptr);
-  else finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, (uint32_t)n0, tab, sc, sc.counts.ptr, t.leaves.ptr);
+  if (direct) STB_TRY(finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.scan.ptr, sc.counts.ptr, t.leaves.ptr));
+  else STB_TRY(finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.scan.ptr, sc.counts.ptr, t.leaves.ptr));
 
   // ---- node levels ----
   t.layers.clear();
@@ -845,48 +960,53 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
 // unit, include/shared_tree.h:305-316) and every chunk runs through all the levels it spans while
 // the next one is still on the PCIe bus; the scan of each level simply continues from the running
 // total.  Only the last chunk's work and the small top of the tree remain after the copy ends.
+// (No singleton filter here: whether a child occurs again is not known before the last chunk.)
 int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
   const int S = t.S;
   const uint64_t n0 = body_len / (uint64_t)S;
-  static const int chunk_log2 = (int)env_u64("STB_STREAM_CHUNK_LOG2", 24);
-  static const uint64_t min_chunks = env_u64("STB_STREAM_MIN_CHUNKS", 4);
+  const int chunk_log2 = (int)t.opt.stream_chunk_log2;
+  const uint64_t min_chunks = t.opt.stream_min_chunks;
+  if (chunk_log2 < 12 || chunk_log2 > 30) return -1;
   const uint64_t C = 1ull << chunk_log2;
-  if (S > 12 || chunk_log2 < 12 || n0 < min_chunks * C || n0 >= 0x7f000000ull) return -1;
+  if (S > 12 || n0 < min_chunks * C || n0 >= (1ull << 30)) return -1;
   const int Lc = chunk_log2 - 11;  // chunked node levels: a chunk still holds 2048 positions at the last one
   cudaStream_t st = t.stream;
   t.clear();
   Scratch& sc = workspace_of(t);
 
-  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), cnt_off(Lc + 2, 0), slot_off(Lc + 2, 0);
+  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), scan_off(Lc + 2, 0), slot_off(Lc + 2, 0);
   n[0] = n0;
   for (int j = 1; j <= Lc; ++j) n[j] = ceil_div(n[j - 1], 2);
   for (int j = 0; j <= Lc; ++j) {
     const uint64_t blocks = ceil_div(n[j], LVL_TILE);
     ptr_off[j + 1] = ptr_off[j] + blocks * LVL_TILE;
     bit_off[j + 1] = bit_off[j] + blocks * (LVL_TILE / 32);
-    cnt_off[j + 1] = cnt_off[j] + blocks + 1;
+    scan_off[j + 1] = scan_off[j] + blocks + 2;
     slot_off[j + 1] = slot_off[j] + (j == 0 ? 0 : (uint64_t)table_cap(n[j]) + 1);
   }
   const uint64_t direct_entries = 1ull << (2 * S);
+  const uint64_t n_top = n[Lc];
   STB_CUDA(t, t.staging.ensure(n0 * (uint64_t)S + 16, st));
   STB_CUDA(t, sc.ptr_arena.ensure(ptr_off[Lc + 1], st));
   STB_CUDA(t, sc.bit_arena.ensure(bit_off[Lc + 1], st));
-  STB_CUDA(t, sc.cnt_arena.ensure(cnt_off[Lc + 1], st));
+  STB_CUDA(t, sc.scan_arena.ensure(scan_off[Lc + 1], st));
   STB_CUDA(t, sc.level_sizes.ensure(Lc + 2, st));
-  STB_CUDA(t, sc.counts.ensure(80, st));
   STB_CUDA(t, sc.flags.ensure(1, st));
-  STB_CUDA(t, sc.root.ensure(1, st));
   STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
   STB_CUDA(t, sc.dids.ensure(direct_entries, st));
+  STB_TRY(reserve_node_workspace(t, sc, n_top));  // the top of the tree, as in the one-shot build
   {
     bool grew = false;
     STB_CUDA(t, sc.stream_slots.ensure(slot_off[Lc + 1], st, &grew));
-    if (grew) {
+    if (grew || !sc.stream_tags_cleared) {
       Launch l(t, "table_clear", false);
       STB_CUDA(t, cudaMemsetAsync(sc.stream_slots.ptr, 0xff, sc.stream_slots.bytes(), st));
+      sc.stream_tags_cleared = true;
+      sc.stream_serial = 0;
     }
   }
   STB_CUDA(t, cudaMemsetAsync(sc.bit_arena.ptr, 0, bit_off[Lc + 1] * 4, st));
+  STB_CUDA(t, cudaMemsetAsync(sc.scan_arena.ptr, 0, scan_off[Lc + 1] * 8, st));
   STB_CUDA(t, cudaMemsetAsync(sc.counts.ptr, 0, 80 * 4, st));
   STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
   {
@@ -904,7 +1024,7 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
     STB_CUDA(t, t.layers.back().nodes.alloc(n[j], st));
   }
   std::vector<uint32_t> serial(Lc + 1, 0);
-  for (int j = 1; j <= Lc; ++j) serial[j] = ++sc.serial;
+  for (int j = 1; j <= Lc; ++j) serial[j] = ++sc.stream_serial;
 
   // all chunk copies are queued at once on their own stream; compute waits chunk by chunk
   if (!sc.copy_stream) STB_CUDA(t, cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
@@ -923,7 +1043,7 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
 
   uint32_t* const ptrs = sc.ptr_arena.ptr;
   uint32_t* const bits = sc.bit_arena.ptr;
-  uint32_t* const cnts = sc.cnt_arena.ptr;
+  unsigned long long* const scans = sc.scan_arena.ptr;
   LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
   leaf_tab.first_bits = bits;
   for (uint64_t c = 0; c < chunks; ++c) {
@@ -937,53 +1057,39 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
       const uint32_t fb = (uint32_t)(begin / LVL_TILE), nbk = (uint32_t)ceil_div(end - begin, LVL_TILE);
       uint32_t* lvl_ptr = ptrs + ptr_off[j];
       uint32_t* lvl_bits = bits + bit_off[j];
-      uint32_t* lvl_cnt = cnts + cnt_off[j];
+      unsigned long long* lvl_scan = scans + scan_off[j];
       LevelTable tab = leaf_tab;
       if (j > 0) {
         tab = LevelTable{sc.stream_slots.ptr + slot_off[j], nullptr, nullptr, table_cap(n[j])};
         tab.first_bits = lvl_bits;
         Launch l(t, "node_insert");
         // placement by child id above the first node layer; child ids are bounded by the child level's size
-        const uint32_t* child_unique = j > 1 ? sc.level_sizes.ptr + (j - 1) : nullptr;
+        const uint32_t* child_unique = (j > 1 && t.opt.locality) ? sc.level_sizes.ptr + (j - 1) : nullptr;
         node_insert_kernel<<<nbk, LVL_THREADS, 0, st>>>(ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], (uint32_t)end, tab, lvl_ptr, child_unique,
-                                                         serial[j], SingletonFilter{}, fb);
+                                                         serial[j], nullptr, nullptr, fb, nullptr);
       }
       {
-        Launch l(t, "bitmask_blockcnt");
-        bitmask_blockcnt_kernel<<<(unsigned)ceil_div((uint64_t)nbk * 32, 256), 256, 0, st>>>(lvl_bits + (uint64_t)fb * (LVL_TILE / 32), nbk, lvl_cnt + fb);
-      }
-      {
-        Launch l(t, "scan_blocks");
-        scan_blocks_kernel<<<1, 1024, 0, st>>>(lvl_cnt + fb, nbk, sc.counts.ptr + j, sc.counts.ptr + j);
-      }
-      {
+        // the level's ticket counter and tile states persist across the chunks: tile fb finds the
+        // inclusive prefix of tile fb - 1, and counts[j] ends up as the level's running total
         Launch l(t, "assign_ids");
         if (j == 0)
-          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, lvl_cnt, t.leaves.ptr, S, nullptr, 0u, fb);
+          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, lvl_scan, fb + nbk - 1, sc.counts.ptr, t.leaves.ptr,
+                                                                       S, nullptr, 0u);
         else
-          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, lvl_cnt, t.layers[j - 1].nodes.ptr, S,
-                                                                ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], fb);
+          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, lvl_scan, fb + nbk - 1, sc.counts.ptr + j,
+                                                                t.layers[j - 1].nodes.ptr, S, ptrs + ptr_off[j - 1], (uint32_t)n[j - 1]);
       }
       {
         Launch l(t, "resolve_ids");
-        if (j == 0) resolve_kernel<true><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)std::min<uint64_t>(n[0], first + cnt), tab, lvl_bits, fb);
-        else resolve_kernel<false><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, fb);
+        if (j == 0)
+          resolve_kernel<RESOLVE_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)std::min<uint64_t>(n[0], first + cnt), tab, lvl_bits, fb,
+                                                                      nullptr, nullptr);
+        else
+          resolve_kernel<RESOLVE_TABLE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)end, tab, lvl_bits, fb, nullptr, nullptr);
       }
     }
   }
   // the top of the tree: everything above the last chunked level, as in the one-shot build
-  const uint64_t n_top = n[Lc];
-  STB_CUDA(t, sc.ptr_a.ensure(n_top, st));
-  STB_CUDA(t, sc.ptr_b.ensure(ceil_div(n_top, 2), st));
-  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n_top, LVL_TILE) * (LVL_TILE / 32), st));
-  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n_top, LVL_TILE) + 1, st));
-  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
-  STB_CUDA(t, sc.filter.ensure(filter_words(ceil_div(n_top, 2)), st));
-  {
-    bool grew = false;
-    STB_CUDA(t, sc.slots.ensure((uint64_t)table_cap(ceil_div(n_top, 2)) + 1, st, &grew));
-    if (grew) sc.tags_cleared = false;
-  }
   STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, ptrs + ptr_off[Lc], n_top * 4, cudaMemcpyDeviceToDevice, st));
   int more = 0;
   uint32_t* cur = nullptr;
@@ -993,15 +1099,18 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
 
 int build_dispatch(Tree& t, const LeafInput& in, uint64_t n0) {
   if (n0 == 0) return t.fail(STB_ERR_EMPTY, "input holds fewer than dna_size bases");
-  if (n0 >= 0xffffffffull) return t.fail(STB_ERR_TOO_LARGE, "more than 2^32-2 leaf positions");
+  // A node level of n positions probes a table of min(2n, 2^29-2) slots; from 2^29 positions on the
+  // table could fill up (an endless probe) long before the index ceiling is reported, and a level's
+  // positions share a word with three flag bits.  2^30 leaf positions = 12.9 Gbp at dna_size 12.
+  if (n0 >= (1ull << 30)) return t.fail(STB_ERR_TOO_LARGE, "2^30 or more leaf positions");
   t.clear();
   const bool try_direct = t.S <= 12;
   if (try_direct) {
     const int s = build_impl(t, in, n0, true);
     if (s != -1) return s;
   }
-  if (n0 > 480000000ull)
-    return t.fail(STB_ERR_TOO_LARGE, "hash-table leaf level supports at most 480M leaf positions in this version");
+  if (n0 > 268000000ull)
+    return t.fail(STB_ERR_TOO_LARGE, "hash-table leaf level supports at most 268M leaf positions in this version");
   return build_impl(t, in, n0, false);
 }
 
@@ -1022,19 +1131,7 @@ int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_leas
     return STB_OK;
   }
   Scratch& sc = workspace_of(t);
-  const uint64_t n1 = ceil_div(n, 2);
-  STB_CUDA(t, sc.ptr_a.ensure(n, st));
-  STB_CUDA(t, sc.ptr_b.ensure(n1, st));
-  STB_CUDA(t, sc.bitmask.ensure(ceil_div(n1, LVL_TILE) * (LVL_TILE / 32), st));
-  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(n1, LVL_TILE) + 1, st));
-  STB_CUDA(t, sc.chunk_sum.ensure(SCAN_MAX_CHUNKS, st));
-  STB_CUDA(t, sc.counts.ensure(80, st));
-  STB_CUDA(t, sc.filter.ensure(filter_words(n1), st));
-  {
-    bool grew = false;
-    STB_CUDA(t, sc.slots.ensure((uint64_t)table_cap(n1) + 1, st, &grew));
-    if (grew) sc.tags_cleared = false;
-  }
+  STB_TRY(reserve_node_workspace(t, sc, n));
   STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, d_ptrs, n * 4, cudaMemcpyDeviceToDevice, st));
   int level = 0;
   uint32_t* cur = nullptr;

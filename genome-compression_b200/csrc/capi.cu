@@ -141,6 +141,32 @@ int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream) {
   return STB_OK;
 }
 
+static uint64_t* option_slot(Options& o, const char* name) {
+  const struct { const char* name; uint64_t* slot; } table[] = {
+      {"bucket_min", &o.bucket_min}, {"bucket_levels", &o.bucket_levels}, {"bucket_cap", &o.bucket_cap}, {"bucket_slack_permille", &o.bucket_slack_permille},
+      {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max},
+      {"stream_chunk_log2", &o.stream_chunk_log2}, {"stream_min_chunks", &o.stream_min_chunks}};
+  for (const auto& e : table)
+    if (std::strcmp(e.name, name) == 0) return e.slot;
+  return nullptr;
+}
+
+int stb_set_option(stb_tree* tree, const char* name, uint64_t value) {
+  if (!tree || !name) return STB_ERR_INVALID_ARG;
+  uint64_t* slot = option_slot(tree->opt, name);
+  if (!slot) return tree->fail(STB_ERR_INVALID_ARG, std::string("unknown option: ") + name);
+  *slot = value;
+  return STB_OK;
+}
+
+int stb_get_option(const stb_tree* tree, const char* name, uint64_t* value) {
+  if (!tree || !name || !value) return STB_ERR_INVALID_ARG;
+  const uint64_t* slot = option_slot(const_cast<stb_tree*>(tree)->opt, name);
+  if (!slot) return tree->fail(STB_ERR_INVALID_ARG, std::string("unknown option: ") + name);
+  *value = *slot;
+  return STB_OK;
+}
+
 int stb_release_workspace(stb_tree* tree) {
   if (!tree) return STB_ERR_INVALID_ARG;
   STB_TRY(use_device(tree));
@@ -172,6 +198,7 @@ int stb_clone(const stb_tree* tree, stb_tree** out) {
   c->root = tree->root;
   c->width = tree->width;
   c->profiling = tree->profiling;
+  c->opt = tree->opt;
   if (tree->built) {
     cudaStream_t st = tree->stream;
     auto fail = [&](cudaError_t e) {

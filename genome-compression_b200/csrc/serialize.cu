@@ -300,6 +300,21 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
     }
   }
   if (host_layers.empty()) return t.fail(STB_ERR_BAD_STREAM, "stream holds no node layer");
+  // A foreign or damaged stream must not make the device follow wild indices (an illegal address
+  // is sticky for the whole process): every non-null child index has to exist in the layer below,
+  // the root in the top layer.  The reference trusts its input (src/shared_tree.cpp:520-538).
+  {
+    uint64_t below = n_leaves;
+    for (size_t k = 0; k < host_layers.size(); ++k) {
+      for (const uint2& nd : host_layers[k]) {
+        const uint32_t l = nd.x & IDX_MASK, r = nd.y & IDX_MASK;
+        if ((l != IDX_MASK && l >= below) || (r != IDX_MASK && r >= below))
+          return t.fail(STB_ERR_BAD_STREAM, "a node of layer " + std::to_string(k) + " points past the end of the layer below");
+      }
+      below = host_layers[k].size();
+    }
+    if ((root & IDX_MASK) >= below) return t.fail(STB_ERR_BAD_STREAM, "the root pointer does not index the top layer");
+  }
   for (auto& hl : host_layers) {
     t.layers.emplace_back();
     Layer& layer = t.layers.back();

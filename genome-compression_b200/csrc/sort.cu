@@ -32,12 +32,23 @@ histogram_kernel(const uint2* __restrict__ nodes, uint32_t n, uint32_t* __restri
 }
 
 __global__ void __launch_bounds__(HS_THREADS)
-max_kernel(const uint32_t* __restrict__ freq, uint32_t n, uint32_t* __restrict__ out) {
-  uint32_t m = 0;
-  for (uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x; i < n; i += gridDim.x * HS_THREADS) m = max(m, freq[i]);
+max_kernel(const uint32_t* __restrict__ freq, uint32_t n, uint32_t* __restrict__ out_max, uint32_t* __restrict__ out_min) {
+  // both ends of the frequency range: an imported tree may hold unreferenced items (frequency 0)
+  uint32_t m = 0, lo = 0xffffffffu;
+  for (uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x; i < n; i += gridDim.x * HS_THREADS) {
+    const uint32_t f = freq[i];
+    m = max(m, f);
+    lo = min(lo, f);
+  }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+  for (int d = 16; d > 0; d >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (m) atomicMax(out_max, m);
+    atomicMin(out_min, lo);
+  }
 }
 
 // ---- stable LSD radix sort, 8-bit digits -----------------------------------------
@@ -264,7 +275,7 @@ int sort_tree(Tree& t) {
     return off;
   };
   std::vector<uint64_t> freq_off(L), newpos_off(L);
-  const uint64_t max_off = carve(L * 4);
+  const uint64_t max_off = carve(2 * L * 4);  // per child layer: largest and smallest frequency
   for (size_t c = 0; c < L; ++c) {
     const uint64_t n = std::max<uint64_t>(child_count(t, c), 1);
     n_max = std::max(n_max, n);
@@ -282,7 +293,9 @@ int sort_tree(Tree& t) {
   auto words = [&](uint64_t off) { return reinterpret_cast<uint32_t*>(arena + off); };
   std::vector<uint32_t*> freq(L), newpos(L);
   uint32_t* d_max = words(max_off);
+  uint32_t* d_min = d_max + L;
   STB_CUDA(t, cudaMemsetAsync(d_max, 0, L * 4, st));
+  STB_CUDA(t, cudaMemsetAsync(d_min, 0xff, L * 4, st));
   for (size_t c = 0; c < L; ++c) {
     freq[c] = words(freq_off[c]);
     newpos[c] = words(newpos_off[c]);
@@ -290,10 +303,10 @@ int sort_tree(Tree& t) {
     const uint32_t n = (uint32_t)child_count(t, c);
     Launch l(t, "freq_max");
     const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(n, HS_THREADS), 1184);
-    max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c], n, d_max + c);
+    max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c], n, d_max + c, d_min + c);
   }
-  std::vector<uint32_t> maxf(L);
-  STB_CUDA(t, cudaMemcpyAsync(maxf.data(), d_max, L * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<uint32_t> maxf(2 * L);
+  STB_CUDA(t, cudaMemcpyAsync(maxf.data(), d_max, 2 * L * 4, cudaMemcpyDeviceToHost, st));
   STB_CUDA(t, cudaStreamSynchronize(st));
 
   // ranks
@@ -301,7 +314,8 @@ int sort_tree(Tree& t) {
   for (size_t c = 0; c < L; ++c) {
     const uint32_t n = (uint32_t)child_count(t, c);
     int passes = 0;
-    for (uint32_t span = maxf[c] ? maxf[c] - 1 : 0; span; span >>= 8) ++passes;  // keys are maxf - freq in [0, maxf-1]
+    const uint32_t minf = std::min(maxf[L + c], maxf[c]);
+    for (uint32_t span = maxf[c] - minf; span; span >>= 8) ++passes;  // keys are maxf - freq in [0, maxf - minf]
     if (passes == 0 || n < 2) continue;  // every frequency equal: stable sort = identity
     permuted[c] = true;
     const uint32_t nblocks = (uint32_t)ceil_div(n, RS_TILE);

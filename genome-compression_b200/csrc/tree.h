@@ -16,7 +16,22 @@ struct Layer {
   uint64_t count = 0;
 };
 
+// Tunables of a handle (stb_set_option).  The defaults are what the benchmarks run; tests lower
+// the thresholds so that the large-input paths run on inputs small enough for the oracle.
+struct Options {
+  uint64_t bucket_min = 1ull << 22;      // node levels with at least this many positions are deduplicated on chip (partition.cu)
+  uint64_t bucket_levels = 1;            // ... and only the first this many node levels of a build
+  uint64_t bucket_cap = 4096;            // records a final bucket may hold (<= 4096, the kernel's shared-memory tile)
+  uint64_t bucket_slack_permille = 125;  // head-room of a first-pass bucket over the mean
+  uint64_t child_filter = 1;             // exact singleton filter from the child level's bitmaps (node levels >= 1)
+  uint64_t locality = 1;                 // slot proportional to a child id above the first node layer
+  uint64_t coop_max = 1ull << 20;        // levels with at most this many pointers run in one cooperative launch
+  uint64_t stream_chunk_log2 = 24;       // leaves per chunk of the streaming host build
+  uint64_t stream_min_chunks = 4;        // smaller host inputs are copied and built in one shot
+};
+
 struct Tree : Ctx {
+  Options opt;
   bool built = false;
   uint64_t n_leaves = 0;
   DevBuf<unsigned long long> leaves;

@@ -47,7 +47,7 @@ enum stb_status {
   STB_ERR_BAD_LEAF = 8,       /* packed leaf with bits set at or above 4*dna_size */
   STB_ERR_OUT_OF_RANGE = 9,   /* index >= width (precondition of operator[], src/shared_tree.cpp:266) */
   STB_ERR_BAD_STREAM = 10,    /* truncated / malformed .dag bytes */
-  STB_ERR_TOO_LARGE = 11      /* more than 2^32-1 leaf positions */
+  STB_ERR_TOO_LARGE = 11      /* 2^30 or more leaf positions */
 };
 
 enum stb_memory { STB_HOST = 0, STB_DEVICE = 1 };
@@ -62,6 +62,13 @@ int stb_clone(const stb_tree* tree, stb_tree** out);
 /* A handle keeps its build workspace (tables, pointer arrays, host-input staging) between
  * builds so that repeated builds allocate nothing; this gives it back early. */
 int stb_release_workspace(stb_tree* tree);
+
+/* Tunables of the build (thresholds between its code paths).  Defaults are the
+ * measured optimum; tests lower them to push small inputs through the large-input paths.
+ * Names: "bucket_min", "bucket_levels", "bucket_cap", "bucket_slack_permille", "child_filter", "locality",
+ * "coop_max", "stream_chunk_log2", "stream_min_chunks".  Unknown name: STB_ERR_INVALID_ARG. */
+int stb_set_option(stb_tree* tree, const char* name, uint64_t value);
+int stb_get_option(const stb_tree* tree, const char* name, uint64_t* value);
 
 /* ---- construction --------------------------------------------------------- */
 /* shared_tree(fasta_reader, bool), src/shared_tree.cpp:207 + the ingest semantics

@@ -1,7 +1,10 @@
-"""Run in a subprocess with environment overrides that force the large-input code paths onto
-inputs small enough for the oracle:
-  STB_FILTER_MIN=1                                  singleton filter of the first node layer
-  STB_STREAM_CHUNK_LOG2=12 STB_STREAM_MIN_CHUNKS=2  streaming (chunked) build from host memory"""
+"""Forces the large-input code paths onto inputs small enough for the oracle, through the
+handle's options (stb_set_option), given as name=value arguments:
+  bucket_min=1                                  on-chip (bucketed) deduplication of the node levels
+  bucket_min=1 bucket_levels=9                  ... of every large-path node level, with the exact singleton filter in front
+  bucket_min=1 bucket_cap=16                    ... with buckets that overflow: the hash-table fallback
+  coop_max=0                                    no cooperative middle launch: every level as separate kernels
+  stream_chunk_log2=12 stream_min_chunks=2      streaming (chunked) build from host memory"""
 import sys
 from pathlib import Path
 
@@ -17,6 +20,14 @@ from oracle.pyoracle import Oracle  # noqa: E402
 def main():
     import torch
     stb, oracle = load_package(), Oracle()
+    options = dict(a.split("=") for a in sys.argv[1:])
+
+    class Tree(stb.SharedTree):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            for name, value in options.items():
+                self.set_option(name, int(value))
+    stb = type("Pkg", (), {"SharedTree": Tree, "synth_genome": staticmethod(stb.synth_genome)})
     for name, S in (("merged", 12), ("humhbb", 5), ("vaccg", 16), ("chmpxx", 1)):
         text = corpus_text(name)
         leaves = oracle.fasta_to_leaves(text, S)
@@ -44,6 +55,22 @@ def main():
         assert host.serialize() == want.serialize(), "host body, synthetic"
     host.sort(); want.sort()
     assert host.serialize() == want.serialize()
+    # one handle, host-streaming and device builds of DIFFERENT inputs interleaved: the two node
+    # tables keep separate epoch counters, a reset of one must not revive tags of the other
+    tree = stb.SharedTree(12)
+    bufs, wants = [], []
+    for seed in (21, 22):
+        b = torch.empty(n, dtype=torch.uint8, device="cuda")
+        stb.synth_genome(b, n, seed=seed, repeat_permille=500)
+        bufs.append(b)
+        wants.append(oracle.build(oracle.fasta_to_leaves(b.cpu().numpy().tobytes(), 12), 12).serialize())
+    small = bufs[0][:400_000].contiguous()
+    want_small = oracle.build(oracle.fasta_to_leaves(small.cpu().numpy().tobytes(), 12), 12).serialize()
+    for which in (0, 0, None, 1, 0, None, 1):
+        if which is None:
+            assert tree.build_from_body(small).serialize() == want_small, "device build between streaming builds"
+        else:
+            assert tree.build_from_body(bufs[which].cpu().numpy().tobytes()).serialize() == wants[which], f"interleaved host build {which}"
     # an IUPAC symbol in the middle: the streaming path must fall back, not mis-build
     text = bytearray(buf[:1_200_000].cpu().numpy().tobytes())
     text[600_001] = ord("N")

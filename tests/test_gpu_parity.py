@@ -237,6 +237,58 @@ def test_synthetic_tree_parity(stb, oracle):
     assert tree.leaf_count() < tree.width() and tree.layer_count(0) < tree.width() // 2  # planted repeats dedup
 
 
+def _synth_record(name):
+    import json
+    from conftest import GOLD
+    return json.loads((GOLD / "synth.json").read_text())[name]
+
+
+@pytest.mark.parametrize("name,entry", [("mid_50mbp", "device"), ("mid_50mbp", "host"), ("large_260mbp", "device"),
+                                        ("large_260mbp", "host"), ("config3_3100mbp", "device"), ("config3_3100mbp", "host")])
+def test_synth_reference_golden(stb, name, entry):
+    """BASELINE.json configs 3 / 5 at FULL size against the UNMODIFIED reference: tests/golden/synth.json holds
+    what oracle/_ref produced for the same generated text (oracle/gen_golden_synth.py): per-layer node counts,
+    sha256 of the leaf table and of every raw node layer, of the stream before and after sort_tree
+    (compress.cpp:183-200, src/shared_tree.cpp:488-513) and of the operator[] answers (:268-291)."""
+    import torch
+    rec = _synth_record(name)
+    n = rec["bases"]
+    free, _ = torch.cuda.mem_get_info()
+    if free < 14 * n + (4 << 30):
+        pytest.skip("not enough free device memory for this size")
+    buf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    stb.synth_genome(buf, n, seed=rec["seed"], repeat_permille=rec["repeat_permille"])
+    tree = stb.SharedTree(12)
+    if entry == "host":  # stb_build_from_body(STB_HOST): the chunked build behind the copy
+        host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host.copy_(buf)
+        torch.cuda.synchronize()
+        tree.build_from_body(host)
+        del host
+    else:
+        tree.build_from_body(buf)
+    del buf
+    assert tree.width() == rec["width"] and tree.depth() == rec["depth"]
+    assert tree.leaf_count() == rec["leaves"] and tree.node_count() == rec["nodes"]
+    assert tree.layer_counts() == rec["layer_counts"]
+    if entry == "device":  # every table, word for word
+        assert hashlib.sha256(tree.leaves().tobytes()).hexdigest() == rec["pre_leaves_sha256"]
+        for k, want in enumerate(rec["pre_layer_sha256"]):
+            assert hashlib.sha256(tree.layer(k).tobytes()).hexdigest() == want, f"node layer {k} differs from the reference's"
+    pre = tree.serialize()
+    assert len(pre) == rec["pre_bytes"] and hashlib.sha256(pre).hexdigest() == rec["pre_sha256"]
+    del pre
+    tree.sort()
+    assert tree.bytes() == rec["post_bytes"]
+    post = tree.serialize()
+    assert hashlib.sha256(post).hexdigest() == rec["post_sha256"]
+    del post
+    idx = stb.query_indices(rec["seed"], rec["queries"], rec["width"])
+    ans = tree.random_access(idx)
+    assert [f"{int(v):x}" for v in ans[:8]] == rec["query_first8"]
+    assert hashlib.sha256(np.ascontiguousarray(ans, dtype="<u8").tobytes()).hexdigest() == rec["query_answers_sha256"]
+
+
 def test_large_properties(stb):
     """Sizes the oracle would not finish quickly: size-independent properties only."""
     import torch
@@ -272,16 +324,22 @@ def test_large_properties(stb):
     assert hashlib.sha256(tree.serialize()).digest() == hashlib.sha256(stream).digest()
 
 
-@pytest.mark.parametrize("env", [{"STB_FILTER_MIN": "1"},
-                                 {"STB_STREAM_CHUNK_LOG2": "12", "STB_STREAM_MIN_CHUNKS": "2"},
-                                 {"STB_STREAM_CHUNK_LOG2": "15", "STB_STREAM_MIN_CHUNKS": "2", "STB_FILTER_MIN": "1"}])
-def test_large_input_paths_forced_small(env):
-    """The singleton filter and the streaming host build, forced onto inputs the oracle can
-    check (tests/forced_paths_check.py)."""
-    import os
+@pytest.mark.parametrize("options", [
+    ["bucket_min=1"],
+    ["bucket_min=1", "bucket_levels=9", "coop_max=0"],
+    ["bucket_min=1", "bucket_cap=16", "bucket_levels=2"],
+    ["coop_max=0"],
+    ["coop_max=0", "child_filter=0", "locality=0"],
+    ["coop_max=65536"],
+    ["stream_chunk_log2=12", "stream_min_chunks=2"],
+    ["stream_chunk_log2=15", "stream_min_chunks=2", "bucket_min=1"],
+])
+def test_large_input_paths_forced_small(options):
+    """The on-chip (bucketed) dedup, its overflow fallback, the cooperative middle launch and the
+    streaming host build, forced onto inputs the oracle can check (tests/forced_paths_check.py)."""
     import subprocess
     import sys
     from conftest import ROOT
-    res = subprocess.run([sys.executable, str(ROOT / "tests" / "forced_paths_check.py")], env=dict(os.environ, **env),
+    res = subprocess.run([sys.executable, str(ROOT / "tests" / "forced_paths_check.py"), *options],
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "forced_paths_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
