@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip sort/serialize/decode/random-access timings")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="stb_set_option on the build handle (experiments; the defaults are what is reported)")
     return ap.parse_args()
 
 
@@ -274,6 +276,9 @@ def run_b200(args):
     pkg.synth_genome(text, n_bases, seed=args.seed, repeat_permille=args.repeat_permille, device=local_rank,
                      stream=stream.cuda_stream)
     tree = pkg.SharedTree(DNA, device=local_rank, stream=stream.cuda_stream)
+    for opt in args.option:
+        name, value = opt.split("=")
+        tree.set_option(name, int(value))
 
     for _ in range(args.warmup):
         tree.build_from_body(text)

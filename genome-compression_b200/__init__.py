@@ -112,6 +112,12 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
+    lib.stb_node_canonical.argtypes = [u32, u32, P(u32), P(u32), P(u32)]
+    lib.stb_node_canonical.restype = None
+    lib.stb_leaf_canonical.argtypes = [u64, i32, P(u32)]
+    lib.stb_leaf_canonical.restype = u64
+    lib.stb_pointer_compose.argtypes = [u32, i32, i32]
+    lib.stb_pointer_compose.restype = u32
     lib.stb_status_string.argtypes = [i32]
     lib.stb_status_string.restype = cp
     lib.stb_last_error.argtypes = [vp]
@@ -340,6 +346,23 @@ def synth_genome(out_device_tensor, n_bases: int, first: int = 0, count: int | N
     if st != 0:
         raise StbError(st, lib.stb_status_string(st).decode())
     return out_device_tensor
+
+
+def node_canonical(left: int, right: int):
+    """node::canonical as the kernels compute it: (left, right, flags >> 29)."""
+    cl, cr, f = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    lib.stb_node_canonical(left, right, C.byref(cl), C.byref(cr), C.byref(f))
+    return cl.value, cr.value, f.value >> 29
+
+
+def leaf_canonical(leaf: int, dna_size: int):
+    f = C.c_uint32()
+    c = lib.stb_leaf_canonical(leaf, dna_size, C.byref(f))
+    return int(c), f.value >> 29
+
+
+def pointer_compose(pointer: int, mirror: int, transpose: int) -> int:
+    return int(lib.stb_pointer_compose(pointer, mirror, transpose))
 
 
 def query_indices(seed: int, queries: int, width: int) -> np.ndarray:

@@ -28,18 +28,18 @@ namespace stb {
 
 namespace {
 
-constexpr int PT_THREADS = 512;
-constexpr int PT_ITEMS = 8;
+constexpr int PT_THREADS = 1024;
+constexpr int PT_ITEMS = 4;
 constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // records per CTA tile
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_MAX_BUCKETS = 512;             // at most 9 bits per pass
+constexpr size_t PT_SMEM = (size_t)PT_TILE * (8 + 4 + 2) + 3 * PT_MAX_BUCKETS * 4;
 
 constexpr int DD_THREADS = 256;
-constexpr int DD_CAP = 4096;                    // records of a final bucket held in shared memory
-constexpr int DD_ITEMS = DD_CAP / DD_THREADS;
-constexpr int DD_SLOTS = 8192;
-constexpr size_t PT_SMEM = (size_t)PT_TILE * 12 + 3 * PT_MAX_BUCKETS * 4;
-constexpr size_t DD_SMEM = (size_t)DD_CAP * 12 + (size_t)DD_SLOTS * 8;
+constexpr int DD_ITEMS = 12;
+constexpr int DD_CAP = DD_THREADS * DD_ITEMS;   // 3072 records of a final bucket, held in registers
+constexpr int DD_SLOTS = 4096;                  // shared-memory table: key 8 B + min-position 4 B per slot
+constexpr size_t DD_SMEM = (size_t)DD_SLOTS * 12 + DD_SLOTS / 8;
 
 __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key) {
   const unsigned long long h = mix64(key);
@@ -49,8 +49,11 @@ __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key
 // One partition pass.  FROM_CHILDREN: the records are made here, from the child pointer array of
 // the level (position p pairs cur[2p], cur[2p+1]; odd tail -> node{last, nullptr}, utility.h:17-29);
 // otherwise blockIdx.y names the first-pass bucket whose records are split.
+// A tile is grouped by bucket in shared memory (rank by a shared-memory atomic per record, one
+// global reservation per bucket and tile) and written out one record per thread, so that the
+// stores of a warp fall into a few contiguous runs.
 template <bool FROM_CHILDREN>
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, 2)
 partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
                  const unsigned long long* __restrict__ in_keys, const uint32_t* __restrict__ in_pos,
                  const uint32_t* __restrict__ in_count, uint32_t in_cap,
@@ -63,22 +66,22 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
   uint32_t* hist = spos + PT_TILE;
   uint32_t* loff = hist + PT_MAX_BUCKETS;
   uint32_t* goff = loff + PT_MAX_BUCKETS;
+  uint16_t* sdig = reinterpret_cast<uint16_t*>(goff + PT_MAX_BUCKETS);
   __shared__ uint32_t warp_sum[PT_WARPS];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nb = 1u << bits;
-  uint32_t count, first;
+  uint32_t count;
+  const uint32_t first = blockIdx.x * PT_TILE;
   uint64_t in_base = 0;
   if (FROM_CHILDREN) {
     count = n_next;
-    first = blockIdx.x * PT_TILE;
   } else {
     count = min(__ldg(in_count + blockIdx.y), in_cap);
-    first = blockIdx.x * PT_TILE;
     if (first >= count) return;
     in_base = (uint64_t)blockIdx.y * in_cap;
   }
-  for (uint32_t i = tid; i < nb; i += PT_THREADS) hist[i] = 0;
+  if (tid < nb) hist[tid] = 0;
   __syncthreads();
 
   unsigned long long key[PT_ITEMS];
@@ -132,9 +135,9 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     }
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    uint32_t before = 0;
-    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
     if (tid < nb) {
+      uint32_t before = 0;
+      for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
       loff[tid] = before + x - c;
       uint32_t g = 0;
       if (c) {
@@ -146,41 +149,44 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     }
   }
   __syncthreads();
+  uint32_t staged = 0;  // records of this tile (valid ones only)
 #pragma unroll
   for (int it = 0; it < PT_ITEMS; ++it) {
     if (dr[it] != 0xffffffffu) {
-      const uint32_t at = loff[dr[it] >> 16] + (dr[it] & 0xffffu);
+      const uint32_t d = dr[it] >> 16, at = loff[d] + (dr[it] & 0xffffu);
       skey[at] = key[it];
       spos[at] = pos[it];
+      sdig[at] = (uint16_t)d;
     }
   }
+  staged = loff[nb - 1] + hist[nb - 1];
   __syncthreads();
-  // a warp writes one bucket's run at a time
-  for (uint32_t d = warp; d < nb; d += PT_WARPS) {
-    const uint32_t c = hist[d];
-    if (c == 0) continue;
-    const uint32_t g = goff[d], src = loff[d];
-    const uint32_t room = g < out_cap ? out_cap - g : 0u;
-    const uint32_t ok = min(c, room);
-    const uint32_t bucket = FROM_CHILDREN ? d : ((blockIdx.y << bits) | d);
-    const uint64_t dst = (uint64_t)bucket * out_cap + g;
-    for (uint32_t i = lane; i < ok; i += 32) {
-      out_keys[dst + i] = skey[src + i];
-      out_pos[dst + i] = spos[src + i];
+#pragma unroll
+  for (int it = 0; it < PT_ITEMS; ++it) {
+    const uint32_t j = it * PT_THREADS + tid;
+    if (j < staged) {
+      const uint32_t d = sdig[j];
+      const uint32_t at = goff[d] + (j - loff[d]);  // place in the bucket's region
+      if (at < out_cap) {
+        const uint32_t bucket = FROM_CHILDREN ? d : ((blockIdx.y << bits) | d);
+        const uint64_t dst = (uint64_t)bucket * out_cap + at;
+        out_keys[dst] = skey[j];
+        out_pos[dst] = spos[j];
+      }
     }
   }
 }
 
-// One CTA per final bucket.
+// One CTA per final bucket.  The records stay in registers; the table (key, min-position per slot)
+// lives in shared memory and is never written back.
 __global__ void __launch_bounds__(DD_THREADS)
 bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ counts,
                     uint32_t cap, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits,
                     const uint32_t* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t smem[];
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
-  uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)DD_CAP * 8);
-  uint32_t* towner = spos + DD_CAP;   // record that claimed the slot (bit 31: the key occurred again)
-  uint32_t* tmin = towner + DD_SLOTS; // smallest position of the slot's key
+  unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem);
+  uint32_t* tmin = reinterpret_cast<uint32_t*>(smem + (size_t)DD_SLOTS * 8);  // smallest position of the slot's key
+  uint32_t* tmulti = tmin + DD_SLOTS;                                         // bit per slot: the key occurred again
   if (*overflow) return;
   const uint32_t tid = threadIdx.x;
   const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
@@ -197,15 +203,12 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
       pos[j] = __ldcs(poss + base + i);
     }
   }
-  for (uint32_t i = tid; i < DD_SLOTS; i += DD_THREADS) {
-    towner[i] = 0xffffffffu;
-    tmin[i] = 0xffffffffu;
-  }
 #pragma unroll
-  for (int j = 0; j < DD_ITEMS; ++j) {
-    const uint32_t i = j * DD_THREADS + tid;
-    if (i < count) skey[i] = key[j];
+  for (int i = 0; i < DD_SLOTS / DD_THREADS; ++i) {
+    tkey[i * DD_THREADS + tid] = EMPTY_KEY;
+    tmin[i * DD_THREADS + tid] = 0xffffffffu;
   }
+  if (tid < DD_SLOTS / 32) tmulti[tid] = 0u;
   __syncthreads();
   uint32_t slot[DD_ITEMS];
 #pragma unroll
@@ -214,11 +217,11 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
     if (i >= count) continue;
     uint32_t h = (uint32_t)bucket_hash(key[j]) & (DD_SLOTS - 1);
     for (;;) {
-      uint32_t o = towner[h];
-      if (o == 0xffffffffu) o = atomicCAS(&towner[h], 0xffffffffu, i);
-      if (o == 0xffffffffu) break;  // claimed
-      if (skey[o & 0x7fffffffu] == key[j]) {
-        if (!(o >> 31)) atomicOr(&towner[h], 0x80000000u);
+      unsigned long long k = tkey[h];
+      if (k == EMPTY_KEY) k = atomicCAS(&tkey[h], EMPTY_KEY, key[j]);
+      if (k == EMPTY_KEY) break;  // claimed
+      if (k == key[j]) {
+        atomicOr(&tmulti[h >> 5], 1u << (h & 31));
         break;
       }
       h = (h + 1) & (DD_SLOTS - 1);
@@ -231,11 +234,11 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   for (int j = 0; j < DD_ITEMS; ++j) {
     const uint32_t i = j * DD_THREADS + tid;
     if (i >= count) continue;
-    const uint32_t p = pos[j], fp = tmin[slot[j]];
+    const uint32_t p = pos[j], h = slot[j], fp = tmin[h];
     if (fp != p) {  // a later occurrence: not a first, and it points at the first
       atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
       atomicOr(aux + p, fp);
-    } else if (towner[slot[j]] >> 31) {
+    } else if ((tmulti[h >> 5] >> (h & 31)) & 1u) {
       atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
     }
   }
@@ -247,14 +250,14 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt) {
   BucketPlan pl;
   pl.n = n;
   pl.cap2 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(opt.bucket_cap, 16), DD_CAP);
-  // mean final bucket = half the capacity or less
+  // mean final bucket = two thirds of the capacity or less (the shared-memory table then runs at <= 50 % load)
   int bits = 2;
-  while (bits < 18 && (n >> bits) > pl.cap2 / 2) ++bits;
+  while (bits < 18 && (n >> bits) > (uint64_t)pl.cap2 * 2 / 3) ++bits;
   pl.b1 = (bits + 1) / 2;
   pl.b2 = bits - pl.b1;
   const uint64_t mean1 = ceil_div(n, 1ull << pl.b1);
   pl.cap1 = (uint32_t)((mean1 + mean1 * opt.bucket_slack_permille / 1000 + 1024 + 3) & ~3ull);
-  pl.usable = (n >> bits) <= pl.cap2 / 2 && n < (1ull << 29);
+  pl.usable = (n >> bits) <= (uint64_t)pl.cap2 * 2 / 3 && n < (1ull << 29);
   return pl;
 }
 

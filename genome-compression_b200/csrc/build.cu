@@ -314,64 +314,71 @@ __device__ __forceinline__ void assign_tile(uint32_t block, uint32_t base, const
   }
 }
 
-// Tile states of the single-pass scan (decoupled look-back): one 64-bit word per tile,
-// (flag << 32) | value; flag 0 = nothing yet, 1 = the tile's own count, 2 = the inclusive prefix.
-// scan[0] is the ticket counter that hands out tiles in launch order, scan[1 + tile] the state.
-constexpr unsigned long long SCAN_AGGREGATE = 1ull << 32, SCAN_INCLUSIVE = 2ull << 32;
+// ids = ranks of the first occurrences in position order.  Two levels of counts instead of a scan:
+// count_kernel leaves the number of first occurrences of every tile in blockcnt[] and adds it to
+// its chunk's total (CHUNK_TILES tiles per chunk); a tile's base is then the sum of the chunk
+// totals before its chunk plus the tile counts before it inside the chunk - at most a thousand
+// L2-resident words per CTA at 3.1 Gbp, and no CTA ever waits for another one.  (A single-pass
+// scan with decoupled look-back was measured here first: with 1024-position tiles the look-back
+// chains through every tile in flight and the kernel was 2-4x slower than this, profiles/README.md.)
+constexpr uint32_t CHUNK_TILES = 256;
 
-__device__ __forceinline__ unsigned long long scan_state_load(const unsigned long long* p) {
-  return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-__device__ __forceinline__ void scan_state_store(unsigned long long* p, unsigned long long v) {
-  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+__device__ __forceinline__ void count_tile(const uint32_t* __restrict__ bitmask, uint32_t tile, uint32_t rel, uint32_t* __restrict__ blockcnt,
+                                           uint32_t* __restrict__ chunkcnt) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t c = __popc(bitmask[(uint64_t)tile * (LVL_TILE / 32) + lane]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if (lane == 0) {
+    blockcnt[rel] = c;
+    if (c) atomicAdd(chunkcnt + rel / CHUNK_TILES, c);
+  }
 }
 
-// ids of one level in ONE pass: every CTA takes the next tile (ticket), publishes the number of
-// first occurrences in it, looks back over its predecessors' states for its base and assigns.
-// The ids are ranks in position order whatever the order the tiles finish in.  A tile only ever
-// waits for tiles with smaller tickets, which are running or done, so the look-back cannot stall.
-// The streaming build continues a level chunk after chunk: its states persist and the first tile
-// of a chunk finds the inclusive prefix the previous chunk left.
+// one warp per tile; tiles [first_block, first_block + nb) of the level, counts indexed from 0
+__global__ void __launch_bounds__(256)
+count_kernel(const uint32_t* __restrict__ bitmask, uint32_t first_block, uint32_t nb, uint32_t* __restrict__ blockcnt,
+             uint32_t* __restrict__ chunkcnt) {
+  const uint32_t rel = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (rel < nb) count_tile(bitmask, first_block + rel, rel, blockcnt, chunkcnt);
+}
+
+// Sum over the CTA of: the chunk totals before tile `rel`'s chunk + the tile counts before it in
+// its chunk.  `red` is shared scratch of LVL_THREADS / 32 words; the caller synchronises before
+// reading the result of the next call into the same scratch.
+__device__ __forceinline__ uint32_t tile_base(uint32_t rel, const uint32_t* __restrict__ blockcnt, const uint32_t* __restrict__ chunkcnt,
+                                              uint32_t* red) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t chunk = rel / CHUNK_TILES, in_chunk = chunk * CHUNK_TILES + threadIdx.x;
+  uint32_t part = in_chunk < rel ? blockcnt[in_chunk] : 0u;
+  for (uint32_t i = threadIdx.x; i < chunk; i += LVL_THREADS) part += chunkcnt[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int w = 0; w < LVL_THREADS / 32; ++w) base += red[w];
+  return base;
+}
+
+// `carry_in` (streaming build): the level's running total before this launch's tiles; the last
+// tile leaves the new total in *total_out (a different word: other CTAs still read carry_in).
 template <int MODE>
 __global__ void __launch_bounds__(LVL_THREADS)
-assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask, unsigned long long* __restrict__ scan,
-              uint32_t last_block, uint32_t* __restrict__ total_out, void* __restrict__ uniq, int S, const uint32_t* __restrict__ children,
-              uint32_t n_children) {
+assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint32_t* __restrict__ bitmask,
+              const uint32_t* __restrict__ blockcnt, const uint32_t* __restrict__ chunkcnt, uint32_t first_block,
+              const uint32_t* __restrict__ carry_in, uint32_t* __restrict__ total_out, void* __restrict__ uniq, int S,
+              const uint32_t* __restrict__ children, uint32_t n_children) {
+  static_assert(CHUNK_TILES == LVL_THREADS, "tile_base reads one tile count per thread");
   __shared__ uint32_t word_pref[33];
-  __shared__ uint32_t s_block, s_base;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_block = (uint32_t)atomicAdd(scan, 1ull);
-  __syncthreads();
-  const uint32_t block = s_block;
-  unsigned long long* state = scan + 1;
+  __shared__ uint32_t red[LVL_THREADS / 32];
+  const uint32_t rel = blockIdx.x, block = first_block + rel;
+  const uint32_t base = tile_base(rel, blockcnt, chunkcnt, red) + (carry_in ? *carry_in : 0u);
   uint32_t words[LVL_ITERS];
   tile_prefix(bitmask, block, n, words, word_pref);
-  if (warp == 0) {
-    const uint32_t total = word_pref[32];
-    if (lane == 0 && block > 0) scan_state_store(state + block, SCAN_AGGREGATE | total);
-    uint32_t base = 0;
-    for (int64_t at = (int64_t)block - 1 - lane;; at -= 32) {
-      // the tile before the first one has the inclusive prefix 0
-      unsigned long long st = at >= 0 ? scan_state_load(state + at) : SCAN_INCLUSIVE;
-      while (__any_sync(0xffffffffu, (st >> 32) == 0)) {
-        if ((st >> 32) == 0) st = scan_state_load(state + at);
-      }
-      const uint32_t inclusive = __ballot_sync(0xffffffffu, (st >> 32) == 2);
-      const uint32_t upto = inclusive ? (uint32_t)__ffs(inclusive) - 1u : 31u;  // nearest tile that already knows its prefix
-      uint32_t v = lane <= upto ? (uint32_t)st : 0u;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      base += v;
-      if (inclusive) break;
-    }
-    if (lane == 0) {
-      scan_state_store(state + block, SCAN_INCLUSIVE | (base + total));
-      s_base = base;
-      if (block == last_block) *total_out = base + total;
-    }
-  }
-  __syncthreads();
-  assign_tile<MODE>(block, s_base, words, word_pref, tmp, n, tab, uniq, S, children, n_children);
+  if (rel == gridDim.x - 1 && threadIdx.x == 0) *total_out = base + word_pref[32];
+  assign_tile<MODE>(block, base, words, word_pref, tmp, n, tab, uniq, S, children, n_children);
 }
 
 // Later occurrences.  RESOLVE_DIRECT (ACGT leaves): the id is in the (L2-sized) id table.
@@ -515,12 +522,13 @@ struct MidLevels {
 __global__ void __launch_bounds__(LVL_THREADS)
 mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels out, Slot* slots, uint32_t serial0, uint32_t* aux,
                   uint32_t* bits0, uint32_t* bits1, uint32_t* multi0, uint32_t* multi1, uint32_t parity, bool first_is_upper,
-                  bool use_filter, bool locality, uint32_t* blockcnt, uint32_t* counts) {
+                  bool use_filter, bool locality, uint32_t* blockcnt, uint32_t chunk_off, uint32_t* counts) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t word_pref[33];
-  __shared__ uint32_t warp_red[LVL_THREADS / 32];
+  __shared__ uint32_t red[LVL_THREADS / 32];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* chunkcnt = blockcnt + chunk_off;
   uint32_t* cur = buf_a;
   uint32_t* nxt = buf_b;
   for (int lv = 0; lv < out.levels; ++lv) {
@@ -537,7 +545,9 @@ mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels ou
     LevelTable tab{slots, nullptr, nullptr, (uint32_t)min((unsigned long long)max(1024u, 2u * n_next), 0x1ffffffeull)};
     tab.first_bits = first_bits;
     const uint32_t* child_unique = (locality && upper) ? counts + lv - 1 : nullptr;
-    // insert
+    // insert (the chunk totals of the previous level are no longer read: clear them for this one)
+    if (lv > 0)
+      for (uint32_t i = blockIdx.x * LVL_THREADS + threadIdx.x; i <= nb / CHUNK_TILES; i += gridDim.x * LVL_THREADS) chunkcnt[i] = 0u;
     for (uint32_t block = blockIdx.x; block < nb; block += gridDim.x) {
 #pragma unroll 1
       for (int it = 0; it < LVL_ITERS; ++it) {
@@ -551,12 +561,8 @@ mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels ou
     grid.sync();
     // first occurrences per tile; the bitmaps of the level after this one (the child bitmaps of
     // this level, no longer needed) are cleared on the way
-    for (uint32_t t = blockIdx.x * (LVL_THREADS / 32) + warp; t < nb; t += gridDim.x * (LVL_THREADS / 32)) {
-      uint32_t c = __popc(first_bits[t * (LVL_TILE / 32) + lane]);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-      if (lane == 0) blockcnt[t] = c;
-    }
+    for (uint32_t t = blockIdx.x * (LVL_THREADS / 32) + warp; t < nb; t += gridDim.x * (LVL_THREADS / 32))
+      count_tile(first_bits, t, t, blockcnt, chunkcnt);
     {
       const uint32_t words_after = (((n_next + 1) / 2 + LVL_TILE - 1) / LVL_TILE) * (LVL_TILE / 32);
       uint32_t* za = par ? bits0 : bits1;
@@ -567,19 +573,12 @@ mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels ou
       }
     }
     grid.sync();
-    // assign: a tile's base is the sum of the counts before it (at most a few thousand: every CTA adds them up itself)
+    // assign
     for (uint32_t block = blockIdx.x; block < nb; block += gridDim.x) {
-      uint32_t part = 0;
-      for (uint32_t i = threadIdx.x; i < block; i += LVL_THREADS) part += blockcnt[i];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-      __syncthreads();  // word_pref / warp_red of the previous tile are no longer read
-      if (lane == 0) warp_red[warp] = part;
+      __syncthreads();  // word_pref / red of the previous tile are no longer read
+      const uint32_t base = tile_base(block, blockcnt, chunkcnt, red);
       uint32_t words[LVL_ITERS];
       tile_prefix(first_bits, block, n_next, words, word_pref);
-      uint32_t base = 0;
-#pragma unroll
-      for (int w = 0; w < LVL_THREADS / 32; ++w) base += warp_red[w];
       if (block == nb - 1 && threadIdx.x == 0) counts[lv] = base + word_pref[32];
       assign_tile<MODE_NODE>(block, base, words, word_pref, nxt, n_next, tab, out.nodes[lv], 0, cur, n_cur);
     }
@@ -615,9 +614,9 @@ struct LeafInput {
 };
 
 struct Scratch {
-  DevBuf<uint32_t> ptr_a, ptr_b, aux, bitmask, counts, dminpos, dids, blockcnt;
+  DevBuf<uint32_t> ptr_a, ptr_b, aux, bitmask, counts, dminpos, dids;
   DevBuf<uint32_t> lvl_bits[2], lvl_multi[2];  // node levels: first occurrences / first occurrences that occur again, by level parity
-  DevBuf<unsigned long long> scan;             // ticket + tile states of the single-pass id scan
+  DevBuf<uint32_t> tilecnt;                    // first occurrences per tile, then per chunk of tiles (count_kernel)
   DevBuf<Slot> slots;
   DevBuf<BuildFlags> flags;
   DevBuf<uint32_t> root;
@@ -632,9 +631,9 @@ struct Scratch {
   uint32_t stream_serial = 0;
 
   // streaming build (host input): every chunked level keeps its own pointer array, bitmap,
-  // scan states and table for the whole build
-  DevBuf<uint32_t> ptr_arena, bit_arena, level_sizes;
-  DevBuf<unsigned long long> scan_arena;
+  // table for the whole build, and a running total per level (two copies: a launch reads one
+  // while its last tile writes the other)
+  DevBuf<uint32_t> ptr_arena, bit_arena, level_sizes, run_totals;
   DevBuf<Slot> stream_slots;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
@@ -677,14 +676,20 @@ void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, ui
 // assign -> resolve for one level whose inserts are already queued.  `aux` is what the inserts
 // left per position, `out` receives the finished pointers (the same array for the leaf level).
 template <int MODE>
-int finish_level(Ctx& ctx, const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, const uint32_t* bitmask, unsigned long long* scan,
+int finish_level(Ctx& ctx, const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, const uint32_t* bitmask, uint32_t* tilecnt,
                  uint32_t* total_out, void* uniq, const uint32_t* children = nullptr, uint32_t n_children = 0, uint32_t* multi_bits = nullptr,
                  const uint32_t* firstpos_unless = nullptr) {
   const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
-  STB_CUDA(ctx, cudaMemsetAsync(scan, 0, ((uint64_t)nb + 1) * 8, ctx.stream));
+  uint32_t* chunkcnt = tilecnt + nb;
+  STB_CUDA(ctx, cudaMemsetAsync(chunkcnt, 0, (nb / CHUNK_TILES + 1) * 4, ctx.stream));
+  {
+    Launch l(ctx, "count_firsts");
+    count_kernel<<<(unsigned)ceil_div((uint64_t)nb * 32, 256), 256, 0, ctx.stream>>>(bitmask, 0u, nb, tilecnt, chunkcnt);
+  }
   {
     Launch l(ctx, "assign_ids");
-    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(out, n, tab, bitmask, scan, nb - 1, total_out, uniq, ctx.S, children, n_children);
+    assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(out, n, tab, bitmask, tilecnt, chunkcnt, 0u, nullptr, total_out, uniq, ctx.S, children,
+                                                            n_children);
   }
   {
     Launch l(ctx, "resolve_ids");
@@ -705,8 +710,10 @@ int reserve_node_workspace(Tree& t, Scratch& sc, uint64_t n_cur) {
   STB_CUDA(t, sc.lvl_multi[0].ensure(bitmap_words(n1), st));
   STB_CUDA(t, sc.lvl_bits[1].ensure(bitmap_words(n2), st));
   STB_CUDA(t, sc.lvl_multi[1].ensure(bitmap_words(n2), st));
-  STB_CUDA(t, sc.scan.ensure(ceil_div(n_cur, LVL_TILE) + 2, st));
-  STB_CUDA(t, sc.blockcnt.ensure(ceil_div(std::min<uint64_t>(n1, std::max<uint64_t>(t.opt.coop_max, SMALL_MAX)), LVL_TILE) + 1, st));
+  {
+    const uint64_t tiles = ceil_div(n_cur, LVL_TILE);
+    STB_CUDA(t, sc.tilecnt.ensure(tiles + tiles / CHUNK_TILES + 2, st));
+  }
   STB_CUDA(t, sc.counts.ensure(80, st));
   STB_CUDA(t, sc.root.ensure(1, st));
   {
@@ -779,8 +786,11 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       bool first_is_upper = level > 0, use_filter = t.opt.child_filter != 0, locality = t.opt.locality != 0;
       Slot* slots = sc.slots.ptr;
       uint32_t *aux = sc.aux.ptr, *b0 = sc.lvl_bits[0].ptr, *b1 = sc.lvl_bits[1].ptr, *m0 = sc.lvl_multi[0].ptr, *m1 = sc.lvl_multi[1].ptr;
-      uint32_t *blockcnt = sc.blockcnt.ptr, *counts = counts_dev + level;
-      void* args[] = {&cur, &nxt, &n_cur32, &out, &slots, &serial0, &aux, &b0, &b1, &m0, &m1, &parity, &first_is_upper, &use_filter, &locality, &blockcnt, &counts};
+      uint32_t *blockcnt = sc.tilecnt.ptr, *counts = counts_dev + level;
+      uint32_t chunk_off = (uint32_t)ceil_div(n_first, LVL_TILE);
+      STB_CUDA(t, cudaMemsetAsync(blockcnt + chunk_off, 0, (chunk_off / CHUNK_TILES + 1) * 4, st));
+      void* args[] = {&cur, &nxt, &n_cur32, &out, &slots, &serial0, &aux, &b0, &b1, &m0, &m1, &parity, &first_is_upper, &use_filter, &locality, &blockcnt,
+                      &chunk_off, &counts};
       const unsigned grid = (unsigned)std::min<uint64_t>(sc.coop_grid, ceil_div(n_first, LVL_TILE));
       Launch l(t, "mid_levels");
       STB_CUDA(t, cudaLaunchCooperativeKernel((const void*)mid_levels_kernel, dim3(grid), dim3(LVL_THREADS), args, 0, st));
@@ -821,7 +831,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       node_insert_kernel<<<nb, LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, sc.aux.ptr, child_unique, ++sc.serial, child_first,
                                                       child_multi, 0u, overflow);
     }
-    STB_TRY(finish_level<MODE_NODE>(t, sc.aux.ptr, nxt, (uint32_t)n_next, nt, first_bits, sc.scan.ptr, counts_dev + level, layer.nodes.ptr, cur,
+    STB_TRY(finish_level<MODE_NODE>(t, sc.aux.ptr, nxt, (uint32_t)n_next, nt, first_bits, sc.tilecnt.ptr, counts_dev + level, layer.nodes.ptr, cur,
                                     (uint32_t)n_cur, multi_bits, overflow));
     std::swap(cur, nxt);
     n_cur = n_next;
@@ -940,8 +950,8 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
     if (direct) leaf_insert_u64_kernel<true><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
     else leaf_insert_u64_kernel<false><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
   }
-  if (direct) STB_TRY(finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.scan.ptr, sc.counts.ptr, t.leaves.ptr));
-  else STB_TRY(finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.scan.ptr, sc.counts.ptr, t.leaves.ptr));
+  if (direct) STB_TRY(finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.tilecnt.ptr, sc.counts.ptr, t.leaves.ptr));
+  else STB_TRY(finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.tilecnt.ptr, sc.counts.ptr, t.leaves.ptr));
 
   // ---- node levels ----
   t.layers.clear();
@@ -974,14 +984,13 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
   t.clear();
   Scratch& sc = workspace_of(t);
 
-  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), scan_off(Lc + 2, 0), slot_off(Lc + 2, 0);
+  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), slot_off(Lc + 2, 0);
   n[0] = n0;
   for (int j = 1; j <= Lc; ++j) n[j] = ceil_div(n[j - 1], 2);
   for (int j = 0; j <= Lc; ++j) {
     const uint64_t blocks = ceil_div(n[j], LVL_TILE);
     ptr_off[j + 1] = ptr_off[j] + blocks * LVL_TILE;
     bit_off[j + 1] = bit_off[j] + blocks * (LVL_TILE / 32);
-    scan_off[j + 1] = scan_off[j] + blocks + 2;
     slot_off[j + 1] = slot_off[j] + (j == 0 ? 0 : (uint64_t)table_cap(n[j]) + 1);
   }
   const uint64_t direct_entries = 1ull << (2 * S);
@@ -989,7 +998,8 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
   STB_CUDA(t, t.staging.ensure(n0 * (uint64_t)S + 16, st));
   STB_CUDA(t, sc.ptr_arena.ensure(ptr_off[Lc + 1], st));
   STB_CUDA(t, sc.bit_arena.ensure(bit_off[Lc + 1], st));
-  STB_CUDA(t, sc.scan_arena.ensure(scan_off[Lc + 1], st));
+  STB_CUDA(t, sc.run_totals.ensure(2 * (Lc + 1), st));
+  STB_CUDA(t, sc.tilecnt.ensure(2 * ceil_div(C, LVL_TILE) + 4, st));  // one chunk's tiles at a time (the node workspace below may ask for more)
   STB_CUDA(t, sc.level_sizes.ensure(Lc + 2, st));
   STB_CUDA(t, sc.flags.ensure(1, st));
   STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
@@ -1006,7 +1016,7 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
     }
   }
   STB_CUDA(t, cudaMemsetAsync(sc.bit_arena.ptr, 0, bit_off[Lc + 1] * 4, st));
-  STB_CUDA(t, cudaMemsetAsync(sc.scan_arena.ptr, 0, scan_off[Lc + 1] * 8, st));
+  STB_CUDA(t, cudaMemsetAsync(sc.run_totals.ptr, 0, 2 * (Lc + 1) * 4, st));
   STB_CUDA(t, cudaMemsetAsync(sc.counts.ptr, 0, 80 * 4, st));
   STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
   {
@@ -1043,7 +1053,6 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
 
   uint32_t* const ptrs = sc.ptr_arena.ptr;
   uint32_t* const bits = sc.bit_arena.ptr;
-  unsigned long long* const scans = sc.scan_arena.ptr;
   LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
   leaf_tab.first_bits = bits;
   for (uint64_t c = 0; c < chunks; ++c) {
@@ -1057,7 +1066,11 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
       const uint32_t fb = (uint32_t)(begin / LVL_TILE), nbk = (uint32_t)ceil_div(end - begin, LVL_TILE);
       uint32_t* lvl_ptr = ptrs + ptr_off[j];
       uint32_t* lvl_bits = bits + bit_off[j];
-      unsigned long long* lvl_scan = scans + scan_off[j];
+      // running total of the level: read from one copy, the new total goes to the other
+      const uint32_t* carry = sc.run_totals.ptr + (c & 1) * (Lc + 1) + j;
+      uint32_t* total = sc.run_totals.ptr + ((c + 1) & 1) * (Lc + 1) + j;
+      uint32_t* tilecnt = sc.tilecnt.ptr;
+      uint32_t* chunkcnt = tilecnt + nbk;
       LevelTable tab = leaf_tab;
       if (j > 0) {
         tab = LevelTable{sc.stream_slots.ptr + slot_off[j], nullptr, nullptr, table_cap(n[j])};
@@ -1068,15 +1081,18 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
         node_insert_kernel<<<nbk, LVL_THREADS, 0, st>>>(ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], (uint32_t)end, tab, lvl_ptr, child_unique,
                                                          serial[j], nullptr, nullptr, fb, nullptr);
       }
+      STB_CUDA(t, cudaMemsetAsync(chunkcnt, 0, (nbk / CHUNK_TILES + 1) * 4, st));
       {
-        // the level's ticket counter and tile states persist across the chunks: tile fb finds the
-        // inclusive prefix of tile fb - 1, and counts[j] ends up as the level's running total
+        Launch l(t, "count_firsts");
+        count_kernel<<<(unsigned)ceil_div((uint64_t)nbk * 32, 256), 256, 0, st>>>(lvl_bits, fb, nbk, tilecnt, chunkcnt);
+      }
+      {
         Launch l(t, "assign_ids");
         if (j == 0)
-          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, lvl_scan, fb + nbk - 1, sc.counts.ptr, t.leaves.ptr,
-                                                                       S, nullptr, 0u);
+          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total, t.leaves.ptr, S,
+                                                                       nullptr, 0u);
         else
-          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, lvl_scan, fb + nbk - 1, sc.counts.ptr + j,
+          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total,
                                                                 t.layers[j - 1].nodes.ptr, S, ptrs + ptr_off[j - 1], (uint32_t)n[j - 1]);
       }
       {
@@ -1089,6 +1105,7 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
       }
     }
   }
+  STB_CUDA(t, cudaMemcpyAsync(sc.counts.ptr, sc.run_totals.ptr + (chunks & 1) * (Lc + 1), (Lc + 1) * 4, cudaMemcpyDeviceToDevice, st));
   // the top of the tree: everything above the last chunked level, as in the one-shot build
   STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, ptrs + ptr_off[Lc], n_top * 4, cudaMemcpyDeviceToDevice, st));
   int more = 0;

@@ -167,6 +167,23 @@ int stb_get_option(const stb_tree* tree, const char* name, uint64_t* value) {
   return STB_OK;
 }
 
+void stb_node_canonical(uint32_t left, uint32_t right, uint32_t* out_left, uint32_t* out_right, uint32_t* out_flags) {
+  uint32_t cl, cr, f;
+  canonical_node(left, right, cl, cr, f);
+  if (out_left) *out_left = cl;
+  if (out_right) *out_right = cr;
+  if (out_flags) *out_flags = f;
+}
+
+uint64_t stb_leaf_canonical(uint64_t leaf, int dna_size, uint32_t* out_flags) {
+  uint32_t f;
+  const unsigned long long c = canonical_leaf(leaf, dna_size, f);
+  if (out_flags) *out_flags = f;
+  return c;
+}
+
+uint32_t stb_pointer_compose(uint32_t pointer, int mirror, int transpose) { return compose(pointer, mirror ? 1u : 0u, transpose ? 1u : 0u); }
+
 int stb_release_workspace(stb_tree* tree) {
   if (!tree) return STB_ERR_INVALID_ARG;
   STB_TRY(use_device(tree));

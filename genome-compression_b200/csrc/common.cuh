@@ -52,11 +52,16 @@ __host__ __device__ __forceinline__ unsigned long long pair_key(uint32_t l, uint
 
 // node::canonical + emplace_node's invariant (reference include/shared_tree.h:115-126,
 // src/shared_tree.cpp:662-672).  Returns the canonical children; flags at bits 29..31.
+// For the pointers this library makes (finish_pointer, PTR_NULL: mirror never set on an invariant
+// target) compose() with constant arguments is an XOR: transposing flips bit 30 unless the
+// pointer is null, mirroring flips bit 29 unless the target is invariant.  The four variants are
+// compared on their 31-bit keys, in the reference's order of preference (identity, transposed,
+// mirrored, inverted: variadic_min keeps the first minimum, utility.h:164-170).
 __host__ __device__ __forceinline__ void canonical_node(uint32_t l, uint32_t r, uint32_t& cl, uint32_t& cr,
                                                         uint32_t& flags) {
-  const uint32_t lt = compose(l, 0, 1), rt = compose(r, 0, 1);
-  const uint32_t lm = compose(l, 1, 0), rm = compose(r, 1, 0);
-  const uint32_t li = compose(l, 1, 1), ri = compose(r, 1, 1);
+  const uint32_t tl = ptr_is_null(l) ? 0u : TRANSPOSE, tr = ptr_is_null(r) ? 0u : TRANSPOSE;
+  const uint32_t ml = (~l >> 2) & MIRROR, mr = (~r >> 2) & MIRROR;
+  const uint32_t lt = l ^ tl, rt = r ^ tr, lm = l ^ ml, rm = r ^ mr;
   unsigned long long best = pair_key(l, r);
   cl = l;
   cr = r;
@@ -65,8 +70,8 @@ __host__ __device__ __forceinline__ void canonical_node(uint32_t l, uint32_t r, 
   if (k < best) { best = k; cl = lt; cr = rt; flags = TRANSPOSE; }
   k = pair_key(rm, lm);                     // (1,0)
   if (k < best) { best = k; cl = rm; cr = lm; flags = MIRROR; }
-  k = pair_key(ri, li);                     // (1,1)
-  if (k < best) { best = k; cl = ri; cr = li; flags = MIRROR | TRANSPOSE; }
+  k = pair_key(rm ^ tr, lm ^ tl);           // (1,1)
+  if (k < best) { best = k; cl = rm ^ tr; cr = lm ^ tl; flags = MIRROR | TRANSPOSE; }
   if ((l & KEY31) == (rm & KEY31)) flags |= INVARIANT;
 }
 

@@ -21,7 +21,7 @@ struct Layer {
 struct Options {
   uint64_t bucket_min = 1ull << 22;      // node levels with at least this many positions are deduplicated on chip (partition.cu)
   uint64_t bucket_levels = 1;            // ... and only the first this many node levels of a build
-  uint64_t bucket_cap = 4096;            // records a final bucket may hold (<= 4096, the kernel's shared-memory tile)
+  uint64_t bucket_cap = 3072;            // records a final bucket may hold (<= 3072, what the dedup kernel keeps in registers)
   uint64_t bucket_slack_permille = 125;  // head-room of a first-pass bucket over the mean
   uint64_t child_filter = 1;             // exact singleton filter from the child level's bitmaps (node levels >= 1)
   uint64_t locality = 1;                 // slot proportional to a child id above the first node layer

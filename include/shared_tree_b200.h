@@ -120,6 +120,17 @@ int stb_decode_ascii(const stb_tree* tree, uint64_t first, uint64_t count, char*
 /* operator[] (src/shared_tree.cpp:268-291), batched: out[i] = tree[index[i]] */
 int stb_random_access(const stb_tree* tree, const uint64_t* index, uint64_t queries, uint64_t* out, int memory);
 
+/* ---- value primitives (no device needed) ------------------------------------------------
+ * The very functions the kernels run (__host__ __device__), callable on the host so that the
+ * arithmetic can be checked against the reference's vectors without a GPU.
+ * node::canonical + emplace_node's invariant (include/shared_tree.h:115-126, src/shared_tree.cpp:662-672):
+ * flags = mirror<<29 | transpose<<30 | invariant<<31. */
+void stb_node_canonical(uint32_t left, uint32_t right, uint32_t* out_left, uint32_t* out_right, uint32_t* out_flags);
+/* dna::canonical (src/dna.cpp:135-143); same flag layout. */
+uint64_t stb_leaf_canonical(uint64_t leaf, int dna_size, uint32_t* out_flags);
+/* pointer{p, mirror, transpose} (src/shared_tree.cpp:76-80) */
+uint32_t stb_pointer_compose(uint32_t pointer, int mirror, int transpose);
+
 /* ---- diagnostics ---------------------------------------------------------------------- */
 const char* stb_status_string(int status);
 /* Details of the last failure on this handle.  For STB_ERR_UNKNOWN_SYMBOL the
