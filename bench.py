@@ -232,6 +232,40 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------- reference goldens
+def golden_record(args, variant="plain"):
+    """What the UNMODIFIED reference produced for this exact workload (tests/golden/synth.json, written by
+    oracle/gen_golden_synth.py in the build container), or None when the workload has no golden."""
+    path = ROOT / "tests" / "golden" / "synth.json"
+    if not path.exists():
+        return None
+    for name, rec in json.loads(path.read_text()).items():
+        if (rec["bases"], rec["seed"], rec["repeat_permille"], rec["variant"], rec["dna_size"]) == (
+                args.bases, args.seed, args.repeat_permille, variant, DNA):
+            return dict(rec, name=name)
+    return None
+
+
+def full_size_reference(gold):
+    """The reference's own build of the WHOLE workload (not a sample), timed once when the golden was made."""
+    if not gold or "reference_timing" not in gold:
+        return None
+    rt = gold["reference_timing"]
+    return {"value": rt["gbp_per_s"], "unit": "Gbp/s", "construct_s": rt["construct_s"], "sort_s": rt["sort_s"], "threads": rt["threads"],
+            "host": rt["host"], "how": rt["how"], "source": "tests/golden/synth.json (oracle/gen_golden_synth.py)"}
+
+
+def check_against_golden(rec, what, got, want):
+    if got != want:
+        raise SystemExit(f"bench.py: {what} differs from the reference's ({rec['name']} in tests/golden/synth.json): "
+                         f"got {got}, the reference has {want}")
+
+
+def sha256_of_device_bytes(t, nbytes):
+    import hashlib
+    return hashlib.sha256(t[:nbytes].cpu().numpy().tobytes()).hexdigest()
+
+
 # ---------------------------------------------------------------------------- algorithmic bytes
 def algorithmic_bytes(n0: int, leaf_unique: int, layer_unique: list[int]):
     """Compulsory HBM bytes per kernel class for one build (DESIGN.md §4): streams only;
@@ -354,6 +388,10 @@ def run_b200(args):
         del host
 
     # ---- the rest of the path at the same size: sort_tree, bytes/serialize, decode, random access ----
+    # every stage with its own roofline (SURVEY §8d algorithmic bytes), and the tree itself checked
+    # against what the unmodified reference built from the same text (tests/golden/synth.json)
+    gold = golden_record(args)
+    parity = {"golden": gold["name"] if gold else None}
     pipeline = None
     if not args.no_pipeline:
         def timed(fn, reps=1):
@@ -370,42 +408,123 @@ def run_b200(args):
             tree.profile(True)
             tree.profile_reset()
             ms, out = timed(fn)
-            ksum = sum(r["ms"] for r in tree.profile_read().values())
+            per_kernel = {k: round(r["ms"], 4) for k, r in tree.profile_read().items()}
             tree.profile(False)
-            return ms, ksum, out
+            return ms, per_kernel, out
+
+        def stage(ms, alg_bytes):
+            gbs = alg_bytes / (ms * 1e-3) / 1e9
+            return {"ms": round(ms, 3), "algorithmic_bytes": int(alg_bytes), "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak_gbs, 4)}
 
         tree.build_from_body(text)
-        sort_first_ms, _ = timed(tree.sort)   # first call: the stream-ordered pool grows by the sort's scratch
+        U = [tree.leaf_count()] + tree.layer_counts()     # unique items: leaves, then node layers bottom-up
+        nodes_total = sum(U[1:])
+        stream_pre = tree.bytes()
+        dag = torch.empty(max(stream_pre, 16) + (64 << 20), dtype=torch.uint8, device="cuda")
+        tree.serialize_into(dag)
+        parity["pre_sort_sha256"] = sha256_of_device_bytes(dag, stream_pre)
+        sort_first_ms, _ = timed(tree.sort)   # first sort on this handle (its scratch was reserved by the build)
         tree.build_from_body(text)
-        sort_ms, sort_kernels_ms, _ = kernel_sum(tree.sort)  # same work on the same unsorted tree, scratch served by the pool
+        sort_ms, sort_kernels, _ = kernel_sum(tree.sort)
         plan_ms, stream_bytes = timed(tree.bytes)
-        dag = torch.empty(stream_bytes + 16, dtype=torch.uint8, device="cuda")
         ser_ms, _ = timed(lambda: tree.serialize_into(dag))
+        parity["post_sort_sha256"] = sha256_of_device_bytes(dag, stream_bytes)
+        parity["layer_counts"] = U[1:]
+        parity["leaves"] = U[0]
         out = torch.empty(n0 * DNA, dtype=torch.uint8, device="cuda")
         dec_first_ms, _ = timed(lambda: tree.decode_ascii(out=out))
-        dec_ms, dec_kernels_ms, _ = kernel_sum(lambda: tree.decode_ascii(out=out))
+        dec_ms, dec_kernels, _ = kernel_sum(lambda: tree.decode_ascii(out=out))
         roundtrip_ok = bool(torch.equal(out, text[: n0 * DNA]))
         del out
         leaves_out = torch.empty(n0, dtype=torch.int64, device="cuda")
         decl_ms, _ = timed(lambda: tree.decode(out=leaves_out))
         q = 10_000_000
-        gen = torch.Generator(device="cuda").manual_seed(args.seed)
-        idx = torch.randint(0, n0, (q,), device="cuda", dtype=torch.int64, generator=gen)
+        idx_host = pkg.query_indices(args.seed, q, n0)   # BASELINE.json config 5: seeded, reproducible on the CPU
+        idx = torch.from_numpy(idx_host.astype("int64")).cuda()
         got = torch.empty(q, dtype=torch.int64, device="cuda")
         ra_ms, _ = timed(lambda: tree.random_access(idx, out=got), reps=3)
         ra_ok = bool(torch.equal(got, leaves_out[idx]))
-        del leaves_out, idx, got, dag
+        import hashlib
+        parity["query_answers_sha256"] = hashlib.sha256(got.cpu().numpy().astype("<u8").tobytes()).hexdigest()
+        del leaves_out, idx, got
+        depth = tree.depth()
+        # sort = histogram read + permute/rewire (read + write) of every node layer and the leaf
+        # table + (freq, index) radix passes, here counted as one 8-byte pass per item; serialize = tables in,
+        # stream out; decode = node layers 0-2 once + 8 B per leaf lookup + text out; random access = depth
+        # node reads + leaf + index + answer per query
+        sort_alg = 8 * nodes_total + 2 * 8 * (nodes_total + U[0]) + 8 * (nodes_total + U[0])
+        ser_alg = 8 * (nodes_total + U[0]) + stream_bytes
+        dec_alg = 8 * sum((n0 + (1 << k) - 1) >> k for k in (1, 2, 3)) + 8 * n0 + n0 * DNA
+        ra_alg = q * (8 * (depth - 1) + 8 + 8 + 8)
         pipeline = {
-            "sort_tree_ms": round(sort_ms, 3), "sort_tree_first_call_ms": round(sort_first_ms, 3),
-            "sort_tree_kernels_ms": round(sort_kernels_ms, 3), "bytes_plan_ms": round(plan_ms, 3), "serialize_ms": round(ser_ms, 3),
-            "stream_bytes": int(stream_bytes), "bits_per_base": round(8.0 * stream_bytes / bases_used, 4),
-            "serialize_gbs": round(stream_bytes / (ser_ms * 1e-3) / 1e9, 1),
-            "decode_ascii_ms": round(dec_ms, 3), "decode_ascii_first_call_ms": round(dec_first_ms, 3),
-            "decode_ascii_kernels_ms": round(dec_kernels_ms, 3), "decode_ascii_gbp_s": round(bases_used / (dec_ms * 1e-3) / 1e9, 1),
-            "decode_leaves_ms": round(decl_ms, 3), "decode_roundtrip_equal": roundtrip_ok,
-            "random_access_queries": q, "random_access_ms": round(ra_ms, 3),
-            "random_access_mq_s": round(q / (ra_ms * 1e-3) / 1e6, 1), "random_access_equal": ra_ok,
+            "sort_tree": dict(stage(sort_ms, sort_alg), first_call_ms=round(sort_first_ms, 3), kernels_ms=sort_kernels),
+            "bytes_plan_ms": round(plan_ms, 3),
+            "serialize": dict(stage(ser_ms + plan_ms, ser_alg), emit_ms=round(ser_ms, 3), stream_bytes=int(stream_bytes),
+                              out_gbs=round(stream_bytes / (ser_ms * 1e-3) / 1e9, 1)),
+            "bits_per_base": round(8.0 * stream_bytes / bases_used, 4),
+            "decode_ascii": dict(stage(dec_ms, dec_alg), first_call_ms=round(dec_first_ms, 3), kernels_ms=dec_kernels,
+                                 gbp_s=round(bases_used / (dec_ms * 1e-3) / 1e9, 1), roundtrip_equal=roundtrip_ok),
+            "decode_leaves_ms": round(decl_ms, 3),
+            "random_access": dict(stage(ra_ms, ra_alg), queries=q, mq_s=round(q / (ra_ms * 1e-3) / 1e6, 1), equal_to_decode=ra_ok),
         }
+
+        # ---- the whole `compress` path end to end (compress.cpp:182-200): pinned host text -> build -> sort_tree ->
+        # bytes -> .dag bytes back in pinned host memory; and the way back: host .dag -> deserialize -> text on the host
+        if not args.no_e2e:
+            host = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
+            host.copy_(text)
+            dag_host = torch.empty(stream_bytes + 16, dtype=torch.uint8, pin_memory=True)
+            torch.cuda.synchronize()
+
+            def compress_once():
+                t0 = time.perf_counter()
+                tree.build_from_body(host)
+                tree.sort()
+                nb_ = tree.bytes()
+                tree.serialize_to_host(dag_host)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0, nb_
+            cold_s, _ = compress_once()
+            warm = [compress_once()[0] for _ in range(max(1, min(args.steps, 3)))]
+            warm_s = sum(warm) / len(warm)
+            parity["e2e_compress_sha256"] = __import__("hashlib").sha256(dag_host[:stream_bytes].numpy().tobytes()).hexdigest()
+            text_host = torch.empty(n0 * DNA, dtype=torch.uint8, pin_memory=True)
+            back = pkg.SharedTree(DNA, device=local_rank, stream=stream.cuda_stream)
+
+            def decompress_once():
+                t0 = time.perf_counter()
+                back.deserialize(dag_host[:stream_bytes].numpy())
+                back.decode_ascii_to_host(text_host)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+            dcold_s = decompress_once()
+            dwarm_s = decompress_once()
+            e2e_roundtrip = bool(torch.equal(text_host, host[: n0 * DNA]))
+            ref_t = (gold or {}).get("reference_timing")
+            pipeline["e2e_compress"] = {
+                "value": bases_used / warm_s / 1e9, "unit": "Gbp/s", "ms": round(warm_s * 1e3, 2), "first_call_ms": round(cold_s * 1e3, 2),
+                "h2d_bytes": n_bases, "d2h_bytes": int(stream_bytes), "path": "stb_build_from_body(HOST) + stb_sort_tree + stb_bytes + stb_serialize(HOST)",
+                "reference_s": round(ref_t["construct_s"] + ref_t["sort_s"], 1) if ref_t else None}
+            pipeline["e2e_decompress"] = {
+                "value": bases_used / dwarm_s / 1e9, "unit": "Gbp/s", "ms": round(dwarm_s * 1e3, 2), "first_call_ms": round(dcold_s * 1e3, 2),
+                "h2d_bytes": int(stream_bytes), "d2h_bytes": n0 * DNA, "roundtrip_equal": e2e_roundtrip,
+                "path": "stb_deserialize(host bytes) + stb_decode_ascii(HOST)"}
+            del host, dag_host, text_host, back
+        del dag
+        if gold:
+            check_against_golden(gold, "per-layer node counts", parity["layer_counts"], gold["layer_counts"])
+            check_against_golden(gold, "leaf count", parity["leaves"], gold["leaves"])
+            check_against_golden(gold, "stream sha256 before sort_tree", parity["pre_sort_sha256"], gold["pre_sha256"])
+            check_against_golden(gold, "stream sha256 after sort_tree", parity["post_sort_sha256"], gold["post_sha256"])
+            check_against_golden(gold, "stream length", int(stream_bytes), gold["post_bytes"])
+            check_against_golden(gold, "sha256 of the 10 M operator[] answers", parity["query_answers_sha256"], gold["query_answers_sha256"])
+            if "e2e_compress_sha256" in parity:
+                check_against_golden(gold, "stream sha256 of the end-to-end compress path", parity["e2e_compress_sha256"], gold["post_sha256"])
+            parity["equal_to_reference"] = True
+    elif gold:
+        counts_now = tree.layer_counts()
+        check_against_golden(gold, "per-layer node counts", counts_now, gold["layer_counts"])
+        parity["layer_counts"] = counts_now
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -414,9 +533,11 @@ def run_b200(args):
         chunk = text[:sample].cpu().numpy().tobytes()
         dt, kind, cores = cpu_build_once(chunk)
         cpu = {"value": sample / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": kind,
-               "sample": f"first {sample} bases of the same sequence, one build, {dt:.1f} s", "host_cpus": os.cpu_count()}
+               "sample": f"first {sample} bases of the same sequence, one build, {dt:.1f} s", "host_cpus": os.cpu_count(),
+               "full_size": full_size_reference(gold)}
 
     line = {
+        "parity": parity,
         "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic", "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -284,6 +284,14 @@ class SharedTree:
         self._check(lib.stb_serialize(self._h, device_tensor.data_ptr(), device_tensor.numel(), DEVICE, C.byref(written)))
         return int(written.value)
 
+    def serialize_to_host(self, host_tensor) -> int:
+        """stb_serialize into caller-owned HOST memory (a pinned torch tensor or a numpy array)."""
+        ptr, n, mem, _keep = _as_input(host_tensor, np.uint8)
+        assert mem == HOST
+        written = C.c_uint64(0)
+        self._check(lib.stb_serialize(self._h, ptr, n, HOST, C.byref(written)))
+        return int(written.value)
+
     def deserialize(self, data: bytes) -> "SharedTree":
         arr = np.frombuffer(data, dtype=np.uint8)
         self._check(lib.stb_deserialize(self._h, arr.ctypes.data, arr.size))
@@ -307,6 +315,14 @@ class SharedTree:
         res = np.zeros(count * self.dna_size, dtype=np.uint8)
         self._check(lib.stb_decode_ascii(self._h, first, count, res.ctypes.data, HOST))
         return res.tobytes()
+
+    def decode_ascii_to_host(self, host_tensor, first: int = 0, count: int | None = None):
+        """stb_decode_ascii into caller-owned HOST memory (a pinned torch tensor or a numpy array)."""
+        count = self.width() - first if count is None else count
+        ptr, n, mem, _keep = _as_input(host_tensor, np.uint8)
+        assert mem == HOST and n >= count * self.dna_size
+        self._check(lib.stb_decode_ascii(self._h, first, count, ptr, HOST))
+        return host_tensor
 
     def random_access(self, index, out=None):
         if out is not None:

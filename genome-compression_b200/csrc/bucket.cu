@@ -28,16 +28,11 @@ namespace stb {
 
 namespace {
 
-constexpr int PT_THREADS = 1024;
-constexpr int PT_ITEMS = 4;
-constexpr int PT_TILE = PT_THREADS * PT_ITEMS;  // records per CTA tile
-constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_ITEMS = 4;                     // records per thread; a CTA tile is PT_ITEMS * its thread count
 constexpr int PT_MAX_BUCKETS = 512;             // at most 9 bits per pass
-constexpr size_t PT_SMEM = (size_t)PT_TILE * (8 + 4 + 2) + 3 * PT_MAX_BUCKETS * 4;
+constexpr size_t pt_smem(int threads) { return (size_t)threads * PT_ITEMS * (8 + 4 + 2) + 3 * PT_MAX_BUCKETS * 4; }
 
-constexpr int DD_THREADS = 256;
-constexpr int DD_ITEMS = 12;
-constexpr int DD_CAP = DD_THREADS * DD_ITEMS;   // 3072 records of a final bucket, held in registers
+constexpr int DD_CAP = 3072;                    // records of a final bucket, held in registers (DD_CAP / threads each)
 constexpr int DD_SLOTS = 4096;                  // shared-memory table: key 8 B + min-position 4 B per slot
 constexpr size_t DD_SMEM = (size_t)DD_SLOTS * 12 + DD_SLOTS / 8;
 
@@ -52,14 +47,19 @@ __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key
 // A tile is grouped by bucket in shared memory (rank by a shared-memory atomic per record, one
 // global reservation per bucket and tile) and written out one record per thread, so that the
 // stores of a warp fall into a few contiguous runs.
-template <bool FROM_CHILDREN>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+// PEER (sharded build, first pass only): bucket d belongs to rank d >> bucket_shift; its records go
+// straight into that rank's memory over NVLink, into the segment reserved for this source, and the
+// positions are global (pos_base + local position).  The counters stay local to the source.
+template <bool FROM_CHILDREN, int PT_THREADS, bool PEER>
+__global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
 partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
                  const unsigned long long* __restrict__ in_keys, const uint32_t* __restrict__ in_pos,
                  const uint32_t* __restrict__ in_count, uint32_t in_cap,
                  unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
                  uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
-                 const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi, uint32_t* __restrict__ overflow) {
+                 const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi, uint32_t* __restrict__ overflow,
+                 uint32_t segs, uint32_t pos_base, PeerDest peer) {
+  constexpr int PT_TILE = PT_THREADS * PT_ITEMS, PT_WARPS = PT_THREADS / 32;
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
   uint32_t* spos = reinterpret_cast<uint32_t*>(smem + (size_t)PT_TILE * 8);
@@ -81,7 +81,7 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     if (first >= count) return;
     in_base = (uint64_t)blockIdx.y * in_cap;
   }
-  if (tid < nb) hist[tid] = 0;
+  for (uint32_t i = tid; i < nb; i += PT_THREADS) hist[i] = 0;
   __syncthreads();
 
   unsigned long long key[PT_ITEMS];
@@ -92,7 +92,7 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     bool valid = i < count;
     dr[it] = 0xffffffffu;
     if (FROM_CHILDREN) {
-      pos[it] = i;
+      pos[it] = pos_base + i;
       // every position starts as a first occurrence; the dedup kernel clears the later ones
       const uint32_t word = __ballot_sync(0xffffffffu, valid);
       if (lane == 0 && word) first_bits[i >> 5] = word;
@@ -141,7 +141,7 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
       loff[tid] = before + x - c;
       uint32_t g = 0;
       if (c) {
-        const uint32_t bucket = FROM_CHILDREN ? tid : ((blockIdx.y << bits) | tid);
+        const uint32_t bucket = FROM_CHILDREN ? tid : (((blockIdx.y / segs) << bits) | tid);
         g = atomicAdd(out_count + bucket, c);
         if (g + c > out_cap) *overflow = 1u;
       }
@@ -168,10 +168,17 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
       const uint32_t d = sdig[j];
       const uint32_t at = goff[d] + (j - loff[d]);  // place in the bucket's region
       if (at < out_cap) {
-        const uint32_t bucket = FROM_CHILDREN ? d : ((blockIdx.y << bits) | d);
-        const uint64_t dst = (uint64_t)bucket * out_cap + at;
-        out_keys[dst] = skey[j];
-        out_pos[dst] = spos[j];
+        if (PEER) {
+          const uint32_t owner = d >> peer.bucket_shift, local = d & ((1u << peer.bucket_shift) - 1u);
+          const uint64_t dst = ((uint64_t)local * peer.world + peer.src) * out_cap + at;
+          reinterpret_cast<unsigned long long*>(peer.base[owner] + peer.keys_off)[dst] = skey[j];
+          reinterpret_cast<uint32_t*>(peer.base[owner] + peer.pos_off)[dst] = spos[j];
+        } else {
+          const uint32_t bucket = FROM_CHILDREN ? d : (((blockIdx.y / segs) << bits) | d);
+          const uint64_t dst = (uint64_t)bucket * out_cap + at;
+          out_keys[dst] = skey[j];
+          out_pos[dst] = spos[j];
+        }
       }
     }
   }
@@ -179,14 +186,18 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
 
 // One CTA per final bucket.  The records stay in registers; the table (key, min-position per slot)
 // lives in shared memory and is never written back.
+// PEER (sharded build): positions are global; position p lives on rank p >> log2_positions, whose
+// aux / bitmaps are reached through its arena (plain REDs over NVLink, no answer travels back).
+template <int DD_THREADS, bool PEER>
 __global__ void __launch_bounds__(DD_THREADS)
 bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ counts,
                     uint32_t cap, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits,
-                    const uint32_t* __restrict__ overflow) {
+                    const uint32_t* __restrict__ overflow, PeerHome home) {
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem);
   uint32_t* tmin = reinterpret_cast<uint32_t*>(smem + (size_t)DD_SLOTS * 8);  // smallest position of the slot's key
   uint32_t* tmulti = tmin + DD_SLOTS;                                         // bit per slot: the key occurred again
+  constexpr int DD_ITEMS = DD_CAP / DD_THREADS;
   if (*overflow) return;
   const uint32_t tid = threadIdx.x;
   const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
@@ -203,19 +214,24 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
       pos[j] = __ldcs(poss + base + i);
     }
   }
-#pragma unroll
-  for (int i = 0; i < DD_SLOTS / DD_THREADS; ++i) {
-    tkey[i * DD_THREADS + tid] = EMPTY_KEY;
-    tmin[i * DD_THREADS + tid] = 0xffffffffu;
+  // the table is as large as this bucket needs (a power of two >= 2 x its records): the level
+  // above the first ones sends few records per bucket and should not pay for a full clear
+  uint32_t slots = 64;
+  while (slots < 2 * count && slots < DD_SLOTS) slots <<= 1;
+  const uint32_t mask = slots - 1;
+  for (uint32_t i = tid; i < slots; i += DD_THREADS) {
+    tkey[i] = EMPTY_KEY;
+    tmin[i] = 0xffffffffu;
   }
   if (tid < DD_SLOTS / 32) tmulti[tid] = 0u;
+  static_assert(DD_SLOTS % DD_THREADS == 0 && DD_CAP % DD_THREADS == 0 && DD_SLOTS / 32 <= DD_THREADS, "tile shapes");
   __syncthreads();
   uint32_t slot[DD_ITEMS];
 #pragma unroll
   for (int j = 0; j < DD_ITEMS; ++j) {
     const uint32_t i = j * DD_THREADS + tid;
     if (i >= count) continue;
-    uint32_t h = (uint32_t)bucket_hash(key[j]) & (DD_SLOTS - 1);
+    uint32_t h = (uint32_t)bucket_hash(key[j]) & mask;
     for (;;) {
       unsigned long long k = tkey[h];
       if (k == EMPTY_KEY) k = atomicCAS(&tkey[h], EMPTY_KEY, key[j]);
@@ -224,7 +240,7 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
         atomicOr(&tmulti[h >> 5], 1u << (h & 31));
         break;
       }
-      h = (h + 1) & (DD_SLOTS - 1);
+      h = (h + 1) & mask;
     }
     atomicMin(&tmin[h], pos[j]);
     slot[j] = h;
@@ -234,8 +250,17 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   for (int j = 0; j < DD_ITEMS; ++j) {
     const uint32_t i = j * DD_THREADS + tid;
     if (i >= count) continue;
-    const uint32_t p = pos[j], h = slot[j], fp = tmin[h];
-    if (fp != p) {  // a later occurrence: not a first, and it points at the first
+    uint32_t p = pos[j];
+    const uint32_t h = slot[j], fp = tmin[h];
+    const bool later = fp != p;
+    if (PEER) {
+      char* base = home.base[p >> home.log2_positions];
+      p &= (1u << home.log2_positions) - 1u;
+      aux = reinterpret_cast<uint32_t*>(base + home.aux_off);
+      first_bits = reinterpret_cast<uint32_t*>(base + home.first_off);
+      multi_bits = reinterpret_cast<uint32_t*>(base + home.multi_off);
+    }
+    if (later) {  // a later occurrence: not a first, and it points at the first
       atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
       atomicOr(aux + p, fp);
     } else if ((tmulti[h >> 5] >> (h & 31)) & 1u) {
@@ -258,7 +283,87 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt) {
   const uint64_t mean1 = ceil_div(n, 1ull << pl.b1);
   pl.cap1 = (uint32_t)((mean1 + mean1 * opt.bucket_slack_permille / 1000 + 1024 + 3) & ~3ull);
   pl.usable = (n >> bits) <= (uint64_t)pl.cap2 * 2 / 3 && n < (1ull << 29);
+  pl.partition_threads = (int)opt.partition_threads;
+  pl.dedup_threads = (int)opt.dedup_threads;
   return pl;
+}
+
+template <int T>
+static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
+                             const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* count1,
+                             uint32_t* count2, uint32_t* overflow) {
+  cudaStream_t st = ctx.stream;
+  constexpr int TILE = T * PT_ITEMS;
+  const size_t smem = pt_smem(T);
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    Launch l(ctx, "bucket_partition");
+    partition_kernel<true, T, false><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(
+        cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits, child_first,
+        child_multi, overflow, 1u, 0u, PeerDest{});
+  }
+  {
+    Launch l(ctx, "bucket_partition");
+    const dim3 grid((unsigned)ceil_div(pl.cap1, TILE), 1u << pl.b1);
+    partition_kernel<false, T, false><<<grid, T, smem, st>>>(nullptr, 0u, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr, ws.pos2.ptr,
+                                                             count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, overflow, 1u,
+                                                             0u, PeerDest{});
+  }
+  return STB_OK;
+}
+
+template <int T>
+static int launch_dedup(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, uint32_t nb, const uint32_t* count2, uint32_t* aux, uint32_t* first_bits,
+                        uint32_t* multi_bits, const uint32_t* overflow) {
+  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  Launch l(ctx, "bucket_dedup");
+  bucket_dedup_kernel<T, false><<<nb, T, DD_SMEM, ctx.stream>>>(ws.keys2.ptr, ws.pos2.ptr, count2, pl.cap2, aux, first_bits, multi_bits, overflow,
+                                                               PeerHome{});
+  return STB_OK;
+}
+
+// ---- sharded build (shard.cu drives these) ---------------------------------------------------
+constexpr int SH_PT = 512, SH_DD = 512;
+
+// Step 1 of a sharded level: this rank's positions -> records in the owners' segments.
+int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* send_count,
+                    uint32_t* overflow) {
+  const size_t smem = pt_smem(SH_PT);
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, SH_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (n_next == 0) return STB_OK;
+  Launch l(ctx, "shard_partition");
+  partition_kernel<true, SH_PT, true><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
+      cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, nullptr, nullptr, send_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, child_first,
+      child_multi, overflow, 1u, pos_base, sb.dest);
+  return STB_OK;
+}
+
+// Step 2 (owner): the received segments -> final buckets -> dedup; the answers go to the positions' home ranks.
+int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, const unsigned long long* seg_keys, const uint32_t* seg_pos,
+                const uint32_t* seg_count, uint32_t* count2, uint32_t* overflow) {
+  cudaStream_t st = ctx.stream;
+  const size_t smem = pt_smem(SH_PT);
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false, SH_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel<SH_DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  const uint32_t local1 = 1u << sb.dest.bucket_shift;  // first-pass buckets this rank owns
+  const uint32_t nb = local1 << sb.b2;
+  STB_CUDA(ctx, ws.keys2.ensure((uint64_t)nb * sb.cap2, st));
+  STB_CUDA(ctx, ws.pos2.ensure((uint64_t)nb * sb.cap2, st));
+  STB_CUDA(ctx, cudaMemsetAsync(count2, 0, (uint64_t)nb * 4, st));
+  {
+    Launch l(ctx, "shard_partition2");
+    const dim3 grid((unsigned)ceil_div(sb.cap_seg, SH_PT * PT_ITEMS), local1 * sb.dest.world);
+    partition_kernel<false, SH_PT, false><<<grid, SH_PT, smem, st>>>(nullptr, 0u, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, ws.keys2.ptr, ws.pos2.ptr,
+                                                                     count2, sb.cap2, 64 - sb.b1 - sb.b2, sb.b2, nullptr, nullptr, nullptr, nullptr,
+                                                                     overflow, sb.dest.world, 0u, PeerDest{});
+  }
+  {
+    Launch l(ctx, "shard_dedup");
+    bucket_dedup_kernel<SH_DD, true><<<nb, SH_DD, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, count2, sb.cap2, nullptr, nullptr, nullptr, overflow, sb.home);
+  }
+  return STB_OK;
 }
 
 int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl) {
@@ -269,15 +374,12 @@ int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl) {
   STB_CUDA(ctx, ws.keys2.ensure(r2, st));
   STB_CUDA(ctx, ws.pos2.ensure(r2, st));
   STB_CUDA(ctx, ws.counters.ensure((1ull << pl.b1) + (1ull << (pl.b1 + pl.b2)) + 1, st));
-  // per device, and cheap: set on every call rather than remembered per process
-  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
   return STB_OK;
 }
 
 int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
-                       const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out) {
+                       const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
+                       uint32_t** overflow_out) {
   cudaStream_t st = ctx.stream;
   STB_TRY(bucket_reserve(ctx, ws, pl));
   const uint32_t nb1 = 1u << pl.b1, nb = 1u << (pl.b1 + pl.b2);
@@ -285,22 +387,13 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, cons
   uint32_t* count2 = count1 + nb1;
   uint32_t* overflow = count2 + nb;
   STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 1) * 4, st));
-  {
-    Launch l(ctx, "bucket_partition");
-    partition_kernel<true><<<(unsigned)ceil_div(n_next, PT_TILE), PT_THREADS, PT_SMEM, st>>>(
-        cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits,
-        child_first, child_multi, overflow);
-  }
-  {
-    Launch l(ctx, "bucket_partition");
-    const dim3 grid((unsigned)ceil_div(pl.cap1, PT_TILE), nb1);
-    partition_kernel<false><<<grid, PT_THREADS, PT_SMEM, st>>>(nullptr, 0u, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr,
-                                                              ws.pos2.ptr, count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, overflow);
-  }
-  {
-    Launch l(ctx, "bucket_dedup");
-    bucket_dedup_kernel<<<nb, DD_THREADS, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, count2, pl.cap2, aux, first_bits, multi_bits, overflow);
-  }
+  if (pl.partition_threads == 512)
+    STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, count1, count2, overflow));
+  else
+    STB_TRY(launch_partitions<1024>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, count1, count2, overflow));
+  if (pl.dedup_threads == 256) STB_TRY(launch_dedup<256>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
+  else if (pl.dedup_threads == 512) STB_TRY(launch_dedup<512>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
+  else STB_TRY(launch_dedup<1024>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   *overflow_out = overflow;
   return STB_OK;
 }

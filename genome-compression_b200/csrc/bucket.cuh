@@ -13,6 +13,31 @@ struct BucketPlan {
   uint32_t cap1 = 0;   // records a first-pass bucket can hold
   uint32_t cap2 = 0;   // records a final bucket can hold (<= the dedup kernel's shared-memory tile)
   bool usable = false; // false: the level is too large for final buckets of cap2 records
+  int partition_threads = 512, dedup_threads = 512;  // CTA shapes (Options)
+};
+
+// ---- sharded build: records and answers travel through peer-mapped memory --------------------
+constexpr int STB_MAX_RANKS = 16;
+
+struct PeerDest {               // where a source's first-pass records go
+  char* base[STB_MAX_RANKS] = {};  // the arena of every rank (own included)
+  uint64_t keys_off = 0, pos_off = 0;  // segment arrays inside an arena
+  uint32_t bucket_shift = 0;    // log2(first-pass buckets per owner): bucket d belongs to rank d >> bucket_shift
+  uint32_t src = 0, world = 1;  // this rank; an owner keeps one segment per (bucket, source)
+};
+
+struct PeerHome {               // where a position's per-position words live
+  char* base[STB_MAX_RANKS] = {};
+  uint64_t aux_off = 0, first_off = 0, multi_off = 0;
+  uint32_t log2_positions = 0;  // positions per rank at this level (a power of two)
+};
+
+struct ShardBuckets {
+  int b1 = 1, b2 = 1;           // hash bits of the two passes (the top log2(world) bits of the first choose the owner)
+  uint32_t cap_seg = 0;         // records one source may send to one first-pass bucket
+  uint32_t cap2 = 0;            // records of a final bucket
+  PeerDest dest;
+  PeerHome home;
 };
 
 struct BucketWorkspace {
@@ -32,5 +57,13 @@ int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan);
 // device flag: non-zero means a bucket overflowed and nothing of the above was produced.
 int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
                        const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out);
+
+// shard.cu drives these: see ShardBuckets.  send_count: this source's per-bucket counters (2^b1, zeroed);
+// seg_*: the segments this rank received ((bucket, source) major, cap_seg records each).
+int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* send_count,
+                    uint32_t* overflow);
+int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, const unsigned long long* seg_keys, const uint32_t* seg_pos,
+                const uint32_t* seg_count, uint32_t* count2, uint32_t* overflow);
 
 }  // namespace stb

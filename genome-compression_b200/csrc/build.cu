@@ -243,14 +243,18 @@ node_insert_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_
                    const uint32_t* __restrict__ child_unique, uint32_t serial, const uint32_t* __restrict__ child_first,
                    const uint32_t* __restrict__ child_multi, uint32_t first_block, const uint32_t* __restrict__ enable) {
   if (enable && !*enable) return;  // the fallback of the on-chip path: runs only when a bucket overflowed
-  // several positions per thread: CTAs that live for one probe each are dispatch-bound
+  // several positions per thread: CTAs that live for one probe each are dispatch-bound; the
+  // fallback is launched with a grid that fits the machine and walks the tiles
+  const uint32_t tiles = (n_next + LVL_TILE - 1) / LVL_TILE;
+  for (uint32_t tile = first_block + blockIdx.x; tile < tiles; tile += gridDim.x) {
 #pragma unroll 1
-  for (int it = 0; it < LVL_ITERS; ++it) {
-    const uint32_t p = (first_block + blockIdx.x) * LVL_TILE + it * LVL_THREADS + threadIdx.x;
-    const bool skipped = p < n_next && node_insert_position(cur, n_cur, p, tab, aux, child_unique, serial, child_first, child_multi);
-    // a warp covers one word of the bitmap: certified singletons are marked with one atomic
-    const uint32_t word = __ballot_sync(0xffffffffu, skipped);
-    if ((threadIdx.x & 31) == 0 && word) atomicOr(tab.first_bits + (p >> 5), word);
+    for (int it = 0; it < LVL_ITERS; ++it) {
+      const uint32_t p = tile * LVL_TILE + it * LVL_THREADS + threadIdx.x;
+      const bool skipped = p < n_next && node_insert_position(cur, n_cur, p, tab, aux, child_unique, serial, child_first, child_multi);
+      // a warp covers one word of the bitmap: certified singletons are marked with one atomic
+      const uint32_t word = __ballot_sync(0xffffffffu, skipped);
+      if ((threadIdx.x & 31) == 0 && word) atomicOr(tab.first_bits + (p >> 5), word);
+    }
   }
 }
 
@@ -828,8 +832,8 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
       // Probe-then-claim measured faster than claim-first on B200 (12.0 vs 13.2 ms per 3.1 Gbp),
       // and chunking the level to keep table lines in L2 did not pay (profiles/README.md).
       Launch l(t, pl.usable ? "bucket_fallback" : "node_insert");
-      node_insert_kernel<<<nb, LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, sc.aux.ptr, child_unique, ++sc.serial, child_first,
-                                                      child_multi, 0u, overflow);
+      node_insert_kernel<<<pl.usable ? std::min(nb, 1184u) : nb, LVL_THREADS, 0, st>>>(cur, (uint32_t)n_cur, (uint32_t)n_next, nt, sc.aux.ptr, child_unique,
+                                                                                        ++sc.serial, child_first, child_multi, 0u, overflow);
     }
     STB_TRY(finish_level<MODE_NODE>(t, sc.aux.ptr, nxt, (uint32_t)n_next, nt, first_bits, sc.tilecnt.ptr, counts_dev + level, layer.nodes.ptr, cur,
                                     (uint32_t)n_cur, multi_bits, overflow));
@@ -893,6 +897,10 @@ int finish_build(Tree& t, Scratch& sc, uint64_t n0, int level, const uint32_t* c
       STB_CUDA(t, cudaMemcpyAsync(exact.ptr, layer.nodes.ptr, layer.count * 8, cudaMemcpyDeviceToDevice, st));
       layer.nodes = std::move(exact);
     }
+  }
+  if (t.opt.reserve_pipeline) {  // so that the first sort_tree / decode of this handle does not stop to allocate
+    STB_TRY(sort_reserve(t));
+    STB_TRY(decode_reserve(t));
   }
   return STB_OK;
 }

@@ -326,6 +326,15 @@ int compute_width(Tree& t) {
   return STB_OK;
 }
 
+int decode_reserve(Tree& t) {
+  if (!t.built || t.width == 0) return STB_OK;
+  const int stop = (int)t.layers.size() >= FUSE ? FUSE : 0;
+  const uint64_t widest = (((t.width - 1) >> stop) + 1) * (stop ? 1 : 2) + 2;
+  STB_CUDA(t, t.decode_a.ensure(widest, t.stream));
+  STB_CUDA(t, t.decode_b.ensure(widest, t.stream));
+  return STB_OK;
+}
+
 int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long long* d_out, char* d_ascii) {
   Tree& t = const_cast<Tree&>(tc);
   if (!t.built) return t.fail(STB_ERR_NOT_BUILT, "tree is empty");
@@ -334,14 +343,16 @@ int decode_range(const Tree& tc, uint64_t first, uint64_t count, unsigned long l
   cudaStream_t st = t.stream;
   const int L = (int)t.layers.size();
   const uint64_t last = first + count - 1;
-  STB_CUDA(t, t.decode_a.ensure(count + 2, st));
-  STB_CUDA(t, t.decode_b.ensure(count + 2, st));
+  // pointer level k refers to node layer k and covers 2^(k+1) leaves; level -1 = leaf pointers
+  const int stop = L >= FUSE ? FUSE : 0;  // pointer levels below `stop` are walked inside the output kernel
+  // the largest pointer array that is ever materialised: the one entering the output kernel
+  const uint64_t widest = ((last >> stop) - (first >> stop) + 1) * (stop ? 1 : 2) + 2;
+  STB_CUDA(t, t.decode_a.ensure(widest, st));
+  STB_CUDA(t, t.decode_b.ensure(widest, st));
   uint32_t* cur = t.decode_a.ptr;
   uint32_t* nxt = t.decode_b.ptr;
   STB_CUDA(t, cudaMemcpyAsync(cur, &t.root, 4, cudaMemcpyHostToDevice, st));
   uint64_t lo_cur = 0;
-  // pointer level k refers to node layer k and covers 2^(k+1) leaves; level -1 = leaf pointers
-  const int stop = L >= FUSE ? FUSE : 0;  // pointer levels below `stop` are walked inside the output kernel
   for (int k = L - 1; k >= stop; --k) {
     const uint64_t lo_next = first >> k, hi_next = last >> k;
     const uint64_t n_next = hi_next - lo_next + 1;

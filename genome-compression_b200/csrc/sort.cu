@@ -33,10 +33,18 @@ histogram_kernel(const uint2* __restrict__ nodes, uint32_t n, uint32_t* __restri
 
 __global__ void __launch_bounds__(HS_THREADS)
 max_kernel(const uint32_t* __restrict__ freq, uint32_t n, uint32_t* __restrict__ out_max, uint32_t* __restrict__ out_min) {
-  // both ends of the frequency range: an imported tree may hold unreferenced items (frequency 0)
+  // both ends of the frequency range: an imported tree may hold unreferenced items (frequency 0).
+  // 16-byte loads (the arrays are carved at 256-byte offsets), the tail word by word.
   uint32_t m = 0, lo = 0xffffffffu;
-  for (uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x; i < n; i += gridDim.x * HS_THREADS) {
-    const uint32_t f = freq[i];
+  const uint32_t n4 = n / 4;
+  const uint4* v4 = reinterpret_cast<const uint4*>(freq);
+  for (uint32_t i = blockIdx.x * HS_THREADS + threadIdx.x; i < n4; i += gridDim.x * HS_THREADS) {
+    const uint4 f = __ldg(v4 + i);
+    m = max(max(m, f.x), max(f.y, max(f.z, f.w)));
+    lo = min(min(lo, f.x), min(f.y, min(f.z, f.w)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - 4 * n4) {
+    const uint32_t f = freq[4 * n4 + threadIdx.x];
     m = max(m, f);
     lo = min(lo, f);
   }
@@ -261,34 +269,57 @@ int histogram_u64(const Tree& t, uint64_t layer, unsigned long long* d_out) {
   return STB_OK;
 }
 
+namespace {
+// All scratch of a sort comes from one arena kept by the handle (grow-only): a sort allocates
+// nothing once the handle has seen a tree of this size.
+struct SortLayout {
+  uint64_t arena_bytes = 0, n_max = 1;
+  uint64_t max_off = 0, hist_off = 0, row_off = 0, ka_off = 0, va_off = 0, kb_off = 0, vb_off = 0;
+  std::vector<uint64_t> freq_off, newpos_off;
+  uint64_t carve(uint64_t bytes) {
+    const uint64_t off = arena_bytes;
+    arena_bytes += (bytes + 255) & ~255ull;
+    return off;
+  }
+  explicit SortLayout(const Tree& t) {
+    const size_t L = t.layers.size();
+    freq_off.resize(L);
+    newpos_off.resize(L);
+    max_off = carve(2 * L * 4);  // per child layer: largest and smallest frequency
+    for (size_t c = 0; c < L; ++c) {
+      const uint64_t n = std::max<uint64_t>(child_count(t, c), 1);
+      n_max = std::max(n_max, n);
+      freq_off[c] = carve(n * 4);
+      newpos_off[c] = carve(n * 4);
+    }
+    const uint64_t nblocks_max = ceil_div(n_max, RS_TILE);
+    hist_off = carve(256 * nblocks_max * 4);
+    row_off = carve(256 * 4);
+    ka_off = carve(n_max * 4);
+    va_off = carve(n_max * 4);
+    kb_off = carve(n_max * 4);
+    vb_off = carve(n_max * 4);
+  }
+};
+}  // namespace
+
+int sort_reserve(Tree& t) {
+  if (!t.built) return STB_OK;
+  const SortLayout lay(t);
+  STB_CUDA(t, t.sort_arena.ensure(lay.arena_bytes, t.stream));
+  return STB_OK;
+}
+
 int sort_tree(Tree& t) {
   if (!t.built) return t.fail(STB_ERR_NOT_BUILT, "sort_tree on an empty tree");
   cudaStream_t st = t.stream;
   const size_t L = t.layers.size();
   // child layer c (0 = leaves, c>0 = node layer c-1) is referenced from node layer c.
-  // All scratch comes from one arena kept by the handle (grow-only): a sort allocates nothing
-  // once the handle has sorted a tree of this size.
-  uint64_t n_max = 1, arena_bytes = 0;
-  auto carve = [&](uint64_t bytes) {
-    const uint64_t off = arena_bytes;
-    arena_bytes += (bytes + 255) & ~255ull;
-    return off;
-  };
-  std::vector<uint64_t> freq_off(L), newpos_off(L);
-  const uint64_t max_off = carve(2 * L * 4);  // per child layer: largest and smallest frequency
-  for (size_t c = 0; c < L; ++c) {
-    const uint64_t n = std::max<uint64_t>(child_count(t, c), 1);
-    n_max = std::max(n_max, n);
-    freq_off[c] = carve(n * 4);
-    newpos_off[c] = carve(n * 4);
-  }
-  const uint64_t nblocks_max = ceil_div(n_max, RS_TILE);
-  const uint64_t hist_off = carve(256 * nblocks_max * 4), row_off = carve(256 * 4);
-  const uint64_t ka_off = carve(n_max * 4), va_off = carve(n_max * 4), kb_off = carve(n_max * 4), vb_off = carve(n_max * 4);
-  uint64_t moved_bytes = t.n_leaves * 8;
-  for (size_t k = 0; k < L; ++k) moved_bytes = std::max<uint64_t>(moved_bytes, t.layers[k].count * sizeof(uint2));
-  const uint64_t moved_off = carve(moved_bytes);
-  STB_CUDA(t, t.sort_arena.ensure(arena_bytes, st));
+  const SortLayout lay(t);
+  const std::vector<uint64_t>&freq_off = lay.freq_off, &newpos_off = lay.newpos_off;
+  const uint64_t max_off = lay.max_off, hist_off = lay.hist_off, row_off = lay.row_off, ka_off = lay.ka_off, va_off = lay.va_off,
+                 kb_off = lay.kb_off, vb_off = lay.vb_off;
+  STB_CUDA(t, t.sort_arena.ensure(lay.arena_bytes, st));
   char* arena = t.sort_arena.ptr;
   auto words = [&](uint64_t off) { return reinterpret_cast<uint32_t*>(arena + off); };
   std::vector<uint32_t*> freq(L), newpos(L);
@@ -302,7 +333,7 @@ int sort_tree(Tree& t) {
     STB_TRY(histogram_into(t, c, freq[c]));
     const uint32_t n = (uint32_t)child_count(t, c);
     Launch l(t, "freq_max");
-    const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(n, HS_THREADS), 1184);
+    const unsigned nb = (unsigned)std::min<uint64_t>(ceil_div(ceil_div(n, 4), HS_THREADS), 1184);
     max_kernel<<<nb, HS_THREADS, 0, st>>>(freq[c], n, d_max + c, d_min + c);
   }
   std::vector<uint32_t> maxf(2 * L);
@@ -348,28 +379,29 @@ int sort_tree(Tree& t) {
     }
   }
 
-  // apply: leaves, then every node layer (the top layer keeps its order, :455/:469); permuted
-  // into the arena, then copied back over the layer's own storage
+  // apply: leaves, then every node layer (the top layer keeps its order, :455/:469).  A layer is
+  // permuted into fresh storage, which then becomes the layer (no copy back).
   if (permuted[0]) {
-    unsigned long long* moved = reinterpret_cast<unsigned long long*>(arena + moved_off);
+    DevBuf<unsigned long long> moved;
+    STB_CUDA(t, moved.alloc(t.n_leaves, st));
     {
       Launch l(t, "permute_leaves");
-      permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0], moved);
+      permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0], moved.ptr);
     }
-    STB_CUDA(t, cudaMemcpyAsync(t.leaves.ptr, moved, t.n_leaves * 8, cudaMemcpyDeviceToDevice, st));
+    t.leaves = std::move(moved);
   }
   for (size_t k = 0; k < L; ++k) {
     const uint32_t* child_map = permuted[k] ? newpos[k] : nullptr;
     const uint32_t* dst_map = (k + 1 < L && permuted[k + 1]) ? newpos[k + 1] : nullptr;
     if (!child_map && !dst_map) continue;
     const uint32_t n = (uint32_t)t.layers[k].count;
-    uint2* moved = reinterpret_cast<uint2*>(arena + moved_off);
+    DevBuf<uint2> moved;
+    STB_CUDA(t, moved.alloc(n, st));
     {
       Launch l(t, "permute_rewire");
-      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved);
+      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved.ptr);
     }
-    Launch l(t, "permute_copy_back", false);
-    STB_CUDA(t, cudaMemcpyAsync(t.layers[k].nodes.ptr, moved, (uint64_t)n * sizeof(uint2), cudaMemcpyDeviceToDevice, st));
+    t.layers[k].nodes = std::move(moved);
   }
   t.plan_valid = false;
   STB_CUDA(t, cudaStreamSynchronize(st));

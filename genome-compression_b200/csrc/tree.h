@@ -22,10 +22,13 @@ struct Options {
   uint64_t bucket_min = 1ull << 22;      // node levels with at least this many positions are deduplicated on chip (partition.cu)
   uint64_t bucket_levels = 1;            // ... and only the first this many node levels of a build
   uint64_t bucket_cap = 3072;            // records a final bucket may hold (<= 3072, what the dedup kernel keeps in registers)
+  uint64_t partition_threads = 512;      // CTA size of the partition passes (512 or 1024; 4 records per thread)
+  uint64_t dedup_threads = 512;          // CTA size of the bucket dedup kernel (256, 512 or 1024)
   uint64_t bucket_slack_permille = 125;  // head-room of a first-pass bucket over the mean
   uint64_t child_filter = 1;             // exact singleton filter from the child level's bitmaps (node levels >= 1)
   uint64_t locality = 1;                 // slot proportional to a child id above the first node layer
   uint64_t coop_max = 1ull << 20;        // levels with at most this many pointers run in one cooperative launch
+  uint64_t reserve_pipeline = 1;         // a build also reserves the scratch of sort_tree and decode (the compress path always sorts)
   uint64_t stream_chunk_log2 = 24;       // leaves per chunk of the streaming host build
   uint64_t stream_min_chunks = 4;        // smaller host inputs are copied and built in one shot
 };
@@ -94,6 +97,7 @@ int dist_leaf_direct_minpos(Ctx& ctx, const char* d_body, uint64_t n_local, uint
 int histogram_layer(const Tree& t, uint64_t layer, DevBuf<uint32_t>& freq);
 int histogram_u64(const Tree& t, uint64_t layer, unsigned long long* d_out);
 int sort_tree(Tree& t);
+int sort_reserve(Tree& t);  // the scratch a sort_tree of this tree will need (kept by the handle)
 
 // serialize.cu ---------------------------------------------------------------------
 int stream_plan(Tree& t);
@@ -102,6 +106,7 @@ int deserialize_tree(Tree& t, const uint8_t* h_bytes, uint64_t len);
 
 // decode.cu ------------------------------------------------------------------------
 int compute_width(Tree& t);
+int decode_reserve(Tree& t);  // the scratch a full decode of this tree will need (kept by the handle)
 int decode_range(const Tree& t, uint64_t first, uint64_t count, unsigned long long* d_out, char* d_ascii);
 int random_access(const Tree& t, const unsigned long long* d_index, uint64_t q, unsigned long long* d_out);
 
