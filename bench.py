@@ -549,17 +549,18 @@ def run_b200(args):
 
 
 def run_b200_dist(args, world, rank, local_rank):
-    """N > 1: the sharded build (genome-compression_b200/dist.py).  Strong scaling: the same
-    3.1 Gbp sequence split over the ranks by leaf range; per level the stage kernels write the
-    (key, position) records straight into their hash owner's memory over NVLink and the owners
-    write the answers back; NCCL carries one 4-byte barrier and the bitmap all-reduce."""
+    """N > 1: the sharded build behind one C-ABI call per rank (csrc/shard.cu, include/shared_tree_b200_dist.h).
+    Strong scaling: the same 3.1 Gbp sequence split over the ranks by leaf range; per level the partition kernel
+    stores the (key, position) records straight into their hash owner's memory over NVLink, the owner deduplicates
+    them on chip and answers with plain REDs into the home rank's words; NCCL carries three barriers and one small
+    all-gather per level.  torch.distributed only hands the communicator id around and reduces the timings."""
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
 
     # NCCL prints its version banner on stdout when the box exports NCCL_DEBUG=VERSION; this
     # program owes its caller exactly one JSON line there, so stdout points at stderr until the
-    # communicator exists.
+    # communicators exist.
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -568,14 +569,18 @@ def run_b200_dist(args, world, rank, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         warm = torch.zeros(1, device="cuda")
         dist.all_reduce(warm)
-        dist.all_to_all_single(torch.empty(world, device="cuda"), torch.zeros(world, device="cuda"))
         torch.cuda.synchronize()
+        pkg = load_package()
+        from genome_compression_b200 import shard
+        stream = torch.cuda.current_stream()
+        me = shard.create_nccl(DNA, device=local_rank, stream=stream.cuda_stream)
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
-    pkg = load_package()
-    from genome_compression_b200.dist import CudaStages, DistBuilder, ShardPlan
+    for opt in args.option:
+        name, value = opt.split("=")
+        me.set_option(name, int(value))
     local_cpus = bind_to_gpu_numa_node(local_rank)
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -584,36 +589,29 @@ def run_b200_dist(args, world, rank, local_rank):
         peak_gbs, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
     n_bases = args.bases
     n_leaves = n_bases // DNA
-    plan = ShardPlan(n_leaves, world)
-    lo, hi = plan.level_range(rank, 0)
-    stream = torch.cuda.current_stream()
-    body = torch.empty(max(16, (hi - lo) * DNA), dtype=torch.uint8, device="cuda")
-    if hi > lo:
-        pkg.synth_genome(body, n_bases, first=lo * DNA, count=(hi - lo) * DNA, seed=args.seed,
-                         repeat_permille=args.repeat_permille, device=local_rank, stream=stream.cuda_stream)
-    stages = CudaStages(pkg, DNA, local_rank, stream=stream.cuda_stream)
-    builder = DistBuilder(stages)
-    tree = None
+    first, count = me.range(n_bases)
+    body = torch.empty(max(16, count), dtype=torch.uint8, device="cuda")
+    if count:
+        pkg.synth_genome(body, n_bases, first=first, count=count, seed=args.seed, repeat_permille=args.repeat_permille,
+                         device=local_rank, stream=stream.cuda_stream)
     for _ in range(args.warmup):
-        tree = builder.build_from_body(body, n_bases)
+        me.build_from_body(body, n_bases)
     torch.cuda.synchronize()
     dist.barrier()
     # rank 0 alone polls NVML, and sparsely (its GPU's clocks go into the line): eight processes
-    # polling every 4 ms contend for the driver and doubled the step time at N = 8 (13.7 against
-    # 6.1 ms); the timed region lasts >= 30 ms, so 12 ms still puts samples inside it
+    # polling every 4 ms contend for the driver and doubled the step time at N = 8 in round 1
     sampler = ClockSampler(local_rank, period_s=0.012) if rank == 0 else None
     if sampler:
         sampler.start()
     launches0 = pkg.kernel_launches()
-    stages.ctx.profile(True)
-    stages.ctx.profile_reset()
-    builder.collectives = 0
+    me.profile_reset()
+    me.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        tree = builder.build_from_body(body, n_bases)
+        me.build_from_body(body, n_bases)
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
@@ -622,30 +620,31 @@ def run_b200_dist(args, world, rank, local_rank):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([pkg.kernel_launches() - launches0], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    prof = stages.ctx.profile_read()
-    stages.ctx.profile(False)
+    prof = me.profile_read()
+    me.profile(False)
     ms_per_step = float(ms.item()) / args.steps
     bases_used = n_leaves * DNA
     value = bases_used / (ms_per_step * 1e-3) / 1e9
 
-    # end to end: every rank's text shard starts in pinned host memory
+    # end to end: every rank's text shard starts in pinned host memory (H2D inside the call)
     e2e = None
     if not args.no_e2e:
         host = torch.empty(body.numel(), dtype=torch.uint8, pin_memory=True)
         host.copy_(body)
-        staging = torch.empty_like(body)
+        torch.cuda.synchronize()
+        me.build_from_body(host, n_bases)
         torch.cuda.synchronize()
         dist.barrier()
         reps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(reps):
-            staging.copy_(host, non_blocking=True)
-            t = builder.build_from_body(staging, n_bases)
-            _ = (t.layer_totals, t.root)
+            me.build_from_body(host, n_bases)
+            _ = me.layer_totals()
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         # for the record: the copies alone, all ranks at once (what PCIe and the host memory give)
+        staging = torch.empty_like(body)
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -653,38 +652,65 @@ def run_b200_dist(args, world, rank, local_rank):
         torch.cuda.synchronize()
         ct = torch.tensor([(time.perf_counter() - t0) / reps], device="cuda", dtype=torch.float64)
         dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        del staging, host
         e2e = {"value": bases_used / float(dt.item()) / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": n_bases,
-               "d2h_bytes_per_step": 12 * len(tree.layer_totals) * world + 4, "ms_per_step": float(dt.item()) * 1e3, "steps": reps,
-               "h2d_copy_alone_ms": round(float(ct.item()) * 1e3, 3), "host_cores_bound_per_rank": local_cpus}
+               "d2h_bytes_per_step": 4 * 48 * world, "ms_per_step": float(dt.item()) * 1e3, "steps": reps,
+               "h2d_copy_alone_ms": round(float(ct.item()) * 1e3, 3), "host_cores_bound_per_rank": local_cpus,
+               "path": "stb_shard_build_from_body(STB_HOST) on every rank"}
 
+    # parity, outside the timed region: the tree gathered on rank 0, sorted, serialized, compared with the reference's
+    me.build_from_body(body, n_bases)
+    totals = me.layer_totals()
+    del body
+    tree = me.gather(stream=stream.cuda_stream)
+    parity = None
     if rank == 0:
+        gold = golden_record(args)
+        parity = {"golden": gold["name"] if gold else None, "leaves": tree.leaf_count(), "layer_counts": tree.layer_counts()}
+        nb_pre = tree.bytes()
+        dag = torch.empty(nb_pre + (64 << 20), dtype=torch.uint8, device="cuda")
+        tree.serialize_into(dag)
+        parity["pre_sort_sha256"] = sha256_of_device_bytes(dag, nb_pre)
+        tree.sort()
+        nb_post = tree.bytes()
+        tree.serialize_into(dag)
+        parity["post_sort_sha256"] = sha256_of_device_bytes(dag, nb_post)
+        parity["stream_bytes"] = nb_post
+        del dag
+        if gold:
+            check_against_golden(gold, "per-layer node counts (sharded build)", parity["layer_counts"], gold["layer_counts"])
+            check_against_golden(gold, "leaf count (sharded build)", parity["leaves"], gold["leaves"])
+            check_against_golden(gold, "stream sha256 before sort_tree (sharded build)", parity["pre_sort_sha256"], gold["pre_sha256"])
+            check_against_golden(gold, "stream sha256 after sort_tree (sharded build)", parity["post_sort_sha256"], gold["post_sha256"])
+            parity["equal_to_reference"] = True
         kernels = {name: {"ms_per_step": round(rec["ms"] / args.steps, 4), "launches_per_step": rec["launches"] // args.steps}
                    for name, rec in prof.items()}
-        # algorithmic bytes of rank 0's share of the two table kernels
-        positions = sum(plan.level_range(0, lv)[1] - plan.level_range(0, lv)[0] for lv in range(plan.sharded_levels()))
-        node_positions = positions - (plan.level_range(0, 0)[1] - plan.level_range(0, 0)[0])  # the ACGT leaf level is not exchanged
-        dom = max((k for k in kernels if k.startswith(("dist_", "peer_"))), key=lambda k: kernels[k]["ms_per_step"])
-        # bytes per record of the stage's streams (key 8, position 4, slot / answer / meta 4, pointer pair 8)
-        alg = {"peer_owner_insert": 16, "peer_owner_answer": 12, "peer_owner_filter": 8, "peer_hist": 8, "peer_scatter": 24,
-               "dist_owner_insert": 16, "dist_owner_answer": 12, "dist_partition_hist": 8, "dist_partition_scatter": 24,
-               "dist_finish_first": 20, "dist_finish_rest": 12}.get(dom, 12) * node_positions
+        # the dominant stage of rank 0 and the record streams it moves (bytes per position of the sharded node levels:
+        # children 8 + record out 12 for the partition; record in 12 + out 12 for the owner's split; record in 12 for the dedup)
+        sharded_node_positions = sum(-(-n_leaves // (1 << l)) for l in range(1, len(totals))) // world
+        per_position = {"shard_partition": 20, "shard_partition2": 24, "shard_dedup": 12, "assign_ids": 20, "shard_resolve": 8, "count_firsts": 1}
+        stage_names = [k for k in kernels if k in per_position]
+        dom = max(stage_names or list(kernels), key=lambda k: kernels[k]["ms_per_step"])
+        alg = per_position.get(dom, 12) * sharded_node_positions
         ach = alg / (kernels[dom]["ms_per_step"] * 1e-3) / 1e9
         line = {
+            "parity": parity,
             "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": workload_config(args, {"sharding": f"{world} ranks x {plan.shard} leaf positions; {builder.exchange} exchange by hash owner + "
-                                                         f"bitmap all-reduce per level; {plan.sharded_levels()} sharded levels, levels of <= "
-                                                         f"{plan.cut} positions on rank 0"}),
+            "config": workload_config(args, {"sharding": f"{world} ranks, contiguous power-of-two aligned leaf ranges; records to their hash owner and "
+                                                         f"answers back through peer-mapped memory (NVLink); {len(totals)} sharded levels, the rest on rank 0"}),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
                          "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
-                         "note": "rank 0's launches of the dominant stage kernel; algorithmic bytes = its record streams"},
-            "cpu_baseline": None, "kernels": kernels, "collectives_per_step": builder.collectives // args.steps,
-            "tree": {"width": n_leaves, "leaves": tree.layer_totals[0], "sharded_layer_nodes": tree.layer_totals[1:]},
+                         "note": "rank 0's launches of its dominant stage kernel; algorithmic bytes = the record streams of its share of the sharded levels"},
+            "cpu_baseline": None, "kernels": kernels,
+            "collectives_per_level": {"barriers": 3, "all_gather_words": world},
+            "tree": {"width": n_leaves, "leaves": totals[0], "sharded_layer_nodes": totals[1:]},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
+    me.close()
     dist.destroy_process_group()
 
 

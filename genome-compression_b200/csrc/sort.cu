@@ -303,11 +303,18 @@ struct SortLayout {
 };
 }  // namespace
 
+static int reserve_spares(Tree& t) {
+  STB_CUDA(t, t.spare_leaves.ensure(t.n_leaves, t.stream));
+  if (t.spare_nodes.size() < t.layers.size()) t.spare_nodes.resize(t.layers.size());
+  for (size_t k = 0; k < t.layers.size(); ++k) STB_CUDA(t, t.spare_nodes[k].ensure(t.layers[k].count, t.stream));
+  return STB_OK;
+}
+
 int sort_reserve(Tree& t) {
   if (!t.built) return STB_OK;
   const SortLayout lay(t);
   STB_CUDA(t, t.sort_arena.ensure(lay.arena_bytes, t.stream));
-  return STB_OK;
+  return reserve_spares(t);
 }
 
 int sort_tree(Tree& t) {
@@ -380,28 +387,26 @@ int sort_tree(Tree& t) {
   }
 
   // apply: leaves, then every node layer (the top layer keeps its order, :455/:469).  A layer is
-  // permuted into fresh storage, which then becomes the layer (no copy back).
+  // permuted into its spare, and the two buffers change roles (no copy back).
+  STB_TRY(reserve_spares(t));
   if (permuted[0]) {
-    DevBuf<unsigned long long> moved;
-    STB_CUDA(t, moved.alloc(t.n_leaves, st));
     {
       Launch l(t, "permute_leaves");
-      permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0], moved.ptr);
+      permute_leaves_kernel<<<(unsigned)ceil_div(t.n_leaves, HS_THREADS), HS_THREADS, 0, st>>>(t.leaves.ptr, (uint32_t)t.n_leaves, newpos[0],
+                                                                                               t.spare_leaves.ptr);
     }
-    t.leaves = std::move(moved);
+    std::swap(t.leaves, t.spare_leaves);
   }
   for (size_t k = 0; k < L; ++k) {
     const uint32_t* child_map = permuted[k] ? newpos[k] : nullptr;
     const uint32_t* dst_map = (k + 1 < L && permuted[k + 1]) ? newpos[k + 1] : nullptr;
     if (!child_map && !dst_map) continue;
     const uint32_t n = (uint32_t)t.layers[k].count;
-    DevBuf<uint2> moved;
-    STB_CUDA(t, moved.alloc(n, st));
     {
       Launch l(t, "permute_rewire");
-      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, moved.ptr);
+      permute_rewire_kernel<<<(unsigned)ceil_div(n, HS_THREADS), HS_THREADS, 0, st>>>(t.layers[k].nodes.ptr, n, child_map, dst_map, t.spare_nodes[k].ptr);
     }
-    t.layers[k].nodes = std::move(moved);
+    std::swap(t.layers[k].nodes, t.spare_nodes[k]);
   }
   t.plan_valid = false;
   STB_CUDA(t, cudaStreamSynchronize(st));

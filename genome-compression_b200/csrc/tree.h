@@ -51,10 +51,16 @@ struct Tree : Ctx {
   // offsets): grow-only as well, so repeated calls on one handle allocate nothing.
   DevBuf<uint32_t> decode_a, decode_b;
   DevBuf<char> sort_arena;
+  // sort_tree permutes a layer into its spare and swaps the two (no copy back, no allocation once
+  // the handle has sorted a tree of this shape)
+  DevBuf<unsigned long long> spare_leaves;
+  std::vector<DevBuf<uint2>> spare_nodes;
   void release_scratch() {
     decode_a.release();
     decode_b.release();
     sort_arena.release();
+    spare_leaves.release();
+    spare_nodes.clear();
   }
 
   // serialization plan cache (per-layer byte totals), invalidated by build / sort

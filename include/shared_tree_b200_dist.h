@@ -144,6 +144,43 @@ int stb_dist_peer_finish(stb_tree* ctx, int kind, const void* items_dev, uint64_
 void* stb_dist_peer_payload(void* arena, int world, uint64_t region_cap);
 int stb_dist_peer_put(stb_tree* ctx, void* dst_dev, const void* src_dev, uint64_t bytes);
 
+/* ==== the sharded build behind ONE call per rank (csrc/shard.cu) ===============================
+ *
+ * tree_constructor::reduce (src/shared_tree.cpp:719-736) is one call; so is a rank's share of the
+ * sharded build.  The library holds the communicator (NCCL, looked up at run time), maps the ranks'
+ * arenas into each other (CUDA IPC) and enqueues every level without reading anything back.
+ * World sizes: powers of two up to 16, all ranks on one node.  ACGT text, dna_size <= 12 (anything
+ * else: use the single-GPU build).  The stage calls above remain for callers that bring their own
+ * collectives (genome-compression_b200/dist.py). */
+typedef struct stb_shard stb_shard; /* opaque: one rank */
+#define STB_SHARD_ID_BYTES 128
+
+/* Rank 0 makes the communicator id; the caller hands the bytes to every rank (any transport). */
+int stb_shard_unique_id(uint8_t id[STB_SHARD_ID_BYTES]);
+/* Collective over the ranks of `id`. */
+int stb_shard_create(stb_shard** out, int device, int dna_size, void* cuda_stream, int rank, int world,
+                     const uint8_t id[STB_SHARD_ID_BYTES]);
+/* `world` virtual ranks in THIS process on one device (each with its own stream), for tests and for boxes
+ * with fewer GPUs than ranks: out[0..world).  Drive each from its own thread. */
+int stb_shard_create_local(stb_shard** out, int world, int device, int dna_size);
+int stb_shard_destroy(stb_shard* shard);
+/* The options of stb_set_option, plus "cut": levels with at most this many positions are finished on rank 0. */
+int stb_shard_set_option(stb_shard* shard, const char* name, uint64_t value);
+/* Which bases of a body of n_bases_total this rank builds from (a contiguous, power-of-two aligned leaf range). */
+int stb_shard_range(const stb_shard* shard, uint64_t n_bases_total, uint64_t* first_base, uint64_t* base_count);
+/* Collective.  body_local: this rank's bases (stb_shard_range), host or device memory. */
+int stb_shard_build_from_body(stb_shard* shard, const char* body_local, uint64_t n_bases_total, int memory);
+/* Unique items of the sharded levels (leaves first), known to every rank after a build. */
+int stb_shard_layer_totals(const stb_shard* shard, uint64_t* out, uint64_t cap, uint64_t* count);
+/* Collective.  Rank 0 receives the complete tree in `out` (any handle from stb_create on its device): the
+ * other ranks pass NULL.  sort_tree / serialize / decode then run on it as on a single-GPU tree. */
+int stb_shard_gather(stb_shard* shard, stb_tree* out);
+const char* stb_shard_last_error(const stb_shard* shard);
+/* Per-kernel device timing of this rank: on = 1 / 0 switches it, on < 0 resets the totals; the totals so far
+ * are read into names / total_ms / launches (up to cap entries; *count = classes). */
+int stb_shard_profile(stb_shard* shard, int on, const char** names, double* total_ms, uint64_t* launches, uint64_t cap,
+                      uint64_t* count);
+
 #ifdef __cplusplus
 }
 #endif
