@@ -47,13 +47,15 @@ __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key
 // A tile is grouped by bucket in shared memory (rank by a shared-memory atomic per record, one
 // global reservation per bucket and tile) and written out one record per thread, so that the
 // stores of a warp fall into a few contiguous runs.
-// PEER (sharded build, first pass only): bucket d belongs to rank d >> bucket_shift; its records go
-// straight into that rank's memory over NVLink, into the segment reserved for this source, and the
-// positions are global (pos_base + local position).  The counters stay local to the source.
+// Sharded build: the first pass is local (positions are global: pos_base + local position; bucket d
+// belongs to rank d >> bucket_shift).  PEER marks the owner's second pass, which PULLS its input: the
+// segment of (bucket, source) is read from the source's memory over NVLink with the same coalesced
+// loads a local segment gets (blockIdx.y = local bucket * world + source).  Nothing is pushed:
+// small scattered stores over NVLink ran at a quarter of the rate of these reads.
 template <bool FROM_CHILDREN, int PT_THREADS, bool PEER>
 __global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
 partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
-                 const unsigned long long* __restrict__ in_keys, const uint32_t* __restrict__ in_pos,
+                 const unsigned long long* in_keys, const uint32_t* in_pos,
                  const uint32_t* __restrict__ in_count, uint32_t in_cap,
                  unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
                  uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
@@ -76,6 +78,14 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
   uint64_t in_base = 0;
   if (FROM_CHILDREN) {
     count = n_next;
+  } else if (PEER) {
+    const uint32_t src = blockIdx.y % peer.world, local = blockIdx.y / peer.world;
+    const uint32_t bucket = (peer.src << peer.bucket_shift) | local;  // this owner's bucket, in the source's numbering
+    count = min(*reinterpret_cast<const volatile uint32_t*>(peer.base[src] + peer.count_off + 4ull * bucket), in_cap);
+    if (first >= count) return;
+    in_keys = reinterpret_cast<const unsigned long long*>(peer.base[src] + peer.keys_off);
+    in_pos = reinterpret_cast<const uint32_t*>(peer.base[src] + peer.pos_off);
+    in_base = (uint64_t)bucket * in_cap;
   } else {
     count = min(__ldg(in_count + blockIdx.y), in_cap);
     if (first >= count) return;
@@ -168,17 +178,10 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
       const uint32_t d = sdig[j];
       const uint32_t at = goff[d] + (j - loff[d]);  // place in the bucket's region
       if (at < out_cap) {
-        if (PEER) {
-          const uint32_t owner = d >> peer.bucket_shift, local = d & ((1u << peer.bucket_shift) - 1u);
-          const uint64_t dst = ((uint64_t)local * peer.world + peer.src) * out_cap + at;
-          reinterpret_cast<unsigned long long*>(peer.base[owner] + peer.keys_off)[dst] = skey[j];
-          reinterpret_cast<uint32_t*>(peer.base[owner] + peer.pos_off)[dst] = spos[j];
-        } else {
-          const uint32_t bucket = FROM_CHILDREN ? d : (((blockIdx.y / segs) << bits) | d);
-          const uint64_t dst = (uint64_t)bucket * out_cap + at;
-          out_keys[dst] = skey[j];
-          out_pos[dst] = spos[j];
-        }
+        const uint32_t bucket = FROM_CHILDREN ? d : (((blockIdx.y / segs) << bits) | d);
+        const uint64_t dst = (uint64_t)bucket * out_cap + at;
+        out_keys[dst] = skey[j];
+        out_pos[dst] = spos[j];
       }
     }
   }
@@ -186,8 +189,10 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
 
 // One CTA per final bucket.  The records stay in registers; the table (key, min-position per slot)
 // lives in shared memory and is never written back.
-// PEER (sharded build): positions are global; position p lives on rank p >> log2_positions, whose
-// aux / bitmaps are reached through its arena (plain REDs over NVLink, no answer travels back).
+// PEER (sharded build): positions are global; position p lives on rank p >> log2_positions.  The
+// answers (a later occurrence and where its key came first; a first occurrence whose key came again)
+// are appended to a list per home rank in THIS rank's memory; the home ranks read their lists after
+// the level's barrier and apply them to their own words (shard.cu: apply_answers_kernel).
 template <int DD_THREADS, bool PEER>
 __global__ void __launch_bounds__(DD_THREADS)
 bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ counts,
@@ -198,6 +203,9 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   uint32_t* tmin = reinterpret_cast<uint32_t*>(smem + (size_t)DD_SLOTS * 8);  // smallest position of the slot's key
   uint32_t* tmulti = tmin + DD_SLOTS;                                         // bit per slot: the key occurred again
   constexpr int DD_ITEMS = DD_CAP / DD_THREADS;
+  __shared__ uint32_t tmin_cnt[STB_MAX_RANKS], tmin_base[STB_MAX_RANKS];  // PEER: answers per home rank
+  const uint32_t* overflow_out = overflow;
+  if (PEER && threadIdx.x < STB_MAX_RANKS) tmin_cnt[threadIdx.x] = 0u;
   if (*overflow) return;
   const uint32_t tid = threadIdx.x;
   const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
@@ -250,21 +258,43 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   for (int j = 0; j < DD_ITEMS; ++j) {
     const uint32_t i = j * DD_THREADS + tid;
     if (i >= count) continue;
-    uint32_t p = pos[j];
-    const uint32_t h = slot[j], fp = tmin[h];
+    const uint32_t p = pos[j], h = slot[j], fp = tmin[h];
     const bool later = fp != p;
+    const bool again = !later && ((tmulti[h >> 5] >> (h & 31)) & 1u);
     if (PEER) {
-      char* base = home.base[p >> home.log2_positions];
-      p &= (1u << home.log2_positions) - 1u;
-      aux = reinterpret_cast<uint32_t*>(base + home.aux_off);
-      first_bits = reinterpret_cast<uint32_t*>(base + home.first_off);
-      multi_bits = reinterpret_cast<uint32_t*>(base + home.multi_off);
-    }
-    if (later) {  // a later occurrence: not a first, and it points at the first
+      // answer = (position << 32) | first position, or | 0xffffffff for "this first occurrence occurs again";
+      // kept in registers until the CTA has reserved room in the lists
+      slot[j] = later ? fp : (again ? 0xffffffffu : 0xfffffffeu);
+      if (later || again) atomicAdd(&tmin_cnt[p >> home.log2_positions], 1u);
+    } else if (later) {  // a later occurrence: not a first, and it points at the first
       atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
       atomicOr(aux + p, fp);
-    } else if ((tmulti[h >> 5] >> (h & 31)) & 1u) {
+    } else if (again) {
       atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
+    }
+  }
+  if (PEER) {
+    __syncthreads();
+    if (tid < STB_MAX_RANKS) {  // one reservation per home rank and CTA
+      const uint32_t c = tmin_cnt[tid];
+      uint32_t at = 0;
+      if (c) {
+        at = atomicAdd(reinterpret_cast<uint32_t*>(home.base[home.self] + home.ans_count_off) + tid, c);
+        if (at + c > home.ans_cap) *const_cast<uint32_t*>(overflow_out) = 1u;
+      }
+      tmin_base[tid] = at;
+      tmin_cnt[tid] = 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < DD_ITEMS; ++j) {
+      const uint32_t i = j * DD_THREADS + tid;
+      if (i >= count || slot[j] == 0xfffffffeu) continue;
+      const uint32_t hr = pos[j] >> home.log2_positions;
+      const uint32_t at = tmin_base[hr] + atomicAdd(&tmin_cnt[hr], 1u);
+      if (at < home.ans_cap)
+        reinterpret_cast<unsigned long long*>(home.base[home.self] + home.ans_off)[(uint64_t)hr * home.ans_cap + at] =
+            ((unsigned long long)pos[j] << 32) | slot[j];
     }
   }
 }
@@ -326,26 +356,25 @@ static int launch_dedup(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, uin
 // ---- sharded build (shard.cu drives these) ---------------------------------------------------
 constexpr int SH_PT = 512, SH_DD = 512;
 
-// Step 1 of a sharded level: this rank's positions -> records in the owners' segments.
+// Step 1 of a sharded level: this rank's positions -> records in its own first-pass buckets (the owners pull them).
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
-                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* send_count,
-                    uint32_t* overflow) {
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, unsigned long long* seg_keys,
+                    uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow) {
   const size_t smem = pt_smem(SH_PT);
-  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, SH_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, SH_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (n_next == 0) return STB_OK;
   Launch l(ctx, "shard_partition");
-  partition_kernel<true, SH_PT, true><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
-      cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, nullptr, nullptr, send_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, child_first,
-      child_multi, overflow, 1u, pos_base, sb.dest);
+  partition_kernel<true, SH_PT, false><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
+      cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, child_first,
+      child_multi, overflow, 1u, pos_base, PeerDest{});
   return STB_OK;
 }
 
-// Step 2 (owner): the received segments -> final buckets -> dedup; the answers go to the positions' home ranks.
-int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, const unsigned long long* seg_keys, const uint32_t* seg_pos,
-                const uint32_t* seg_count, uint32_t* count2, uint32_t* overflow) {
+// Step 2 (owner): every rank's segments for this owner -> final buckets -> dedup; the answers go into per-home lists.
+int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, uint32_t* count2, uint32_t* overflow) {
   cudaStream_t st = ctx.stream;
   const size_t smem = pt_smem(SH_PT);
-  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false, SH_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false, SH_PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel<SH_DD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
   const uint32_t local1 = 1u << sb.dest.bucket_shift;  // first-pass buckets this rank owns
   const uint32_t nb = local1 << sb.b2;
@@ -355,9 +384,9 @@ int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, const uns
   {
     Launch l(ctx, "shard_partition2");
     const dim3 grid((unsigned)ceil_div(sb.cap_seg, SH_PT * PT_ITEMS), local1 * sb.dest.world);
-    partition_kernel<false, SH_PT, false><<<grid, SH_PT, smem, st>>>(nullptr, 0u, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, ws.keys2.ptr, ws.pos2.ptr,
-                                                                     count2, sb.cap2, 64 - sb.b1 - sb.b2, sb.b2, nullptr, nullptr, nullptr, nullptr,
-                                                                     overflow, sb.dest.world, 0u, PeerDest{});
+    partition_kernel<false, SH_PT, true><<<grid, SH_PT, smem, st>>>(nullptr, 0u, 0u, nullptr, nullptr, nullptr, sb.cap_seg, ws.keys2.ptr, ws.pos2.ptr, count2,
+                                                                    sb.cap2, 64 - sb.b1 - sb.b2, sb.b2, nullptr, nullptr, nullptr, nullptr, overflow,
+                                                                    sb.dest.world, 0u, sb.dest);
   }
   {
     Launch l(ctx, "shard_dedup");

@@ -19,17 +19,19 @@ struct BucketPlan {
 // ---- sharded build: records and answers travel through peer-mapped memory --------------------
 constexpr int STB_MAX_RANKS = 16;
 
-struct PeerDest {               // where a source's first-pass records go
+struct PeerDest {               // the first-pass buckets of every rank (a source keeps what it makes; owners pull)
   char* base[STB_MAX_RANKS] = {};  // the arena of every rank (own included)
-  uint64_t keys_off = 0, pos_off = 0;  // segment arrays inside an arena
+  uint64_t keys_off = 0, pos_off = 0, count_off = 0;  // bucket arrays and their record counts inside an arena
   uint32_t bucket_shift = 0;    // log2(first-pass buckets per owner): bucket d belongs to rank d >> bucket_shift
-  uint32_t src = 0, world = 1;  // this rank; an owner keeps one segment per (bucket, source)
+  uint32_t src = 0, world = 1;  // this rank
 };
 
-struct PeerHome {               // where a position's per-position words live
+struct PeerHome {               // where the answers about a position go: a list per home rank, in the owner's arena
   char* base[STB_MAX_RANKS] = {};
-  uint64_t aux_off = 0, first_off = 0, multi_off = 0;
-  uint32_t log2_positions = 0;  // positions per rank at this level (a power of two)
+  uint64_t ans_off = 0, ans_count_off = 0;
+  uint32_t ans_cap = 0;         // answers one owner can hold for one home rank
+  uint32_t self = 0;
+  uint32_t log2_positions = 0;  // positions per rank at this level (a power of two): home = position >> log2_positions
 };
 
 struct ShardBuckets {
@@ -58,12 +60,11 @@ int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan);
 int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
                        const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out);
 
-// shard.cu drives these: see ShardBuckets.  send_count: this source's per-bucket counters (2^b1, zeroed);
-// seg_*: the segments this rank received ((bucket, source) major, cap_seg records each).
+// shard.cu drives these: see ShardBuckets.  seg_*: this rank's first-pass buckets (2^b1 x cap_seg records and
+// their counts, in its arena); the owner's split reads every rank's through `dest`.
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
-                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* send_count,
-                    uint32_t* overflow);
-int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, const unsigned long long* seg_keys, const uint32_t* seg_pos,
-                const uint32_t* seg_count, uint32_t* count2, uint32_t* overflow);
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, unsigned long long* seg_keys,
+                    uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow);
+int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, uint32_t* count2, uint32_t* overflow);
 
 }  // namespace stb

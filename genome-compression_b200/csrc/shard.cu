@@ -317,13 +317,26 @@ __global__ void __launch_bounds__(256) leaf_pointers_kernel(uint32_t* __restrict
   tmp[i] = finish_pointer(__ldcg(ids + (t & IDX_MASK)), t & ~IDX_MASK);
 }
 
-// a source tells every owner how many records it sent to each of the owner's buckets
-__global__ void __launch_bounds__(256) publish_counts_kernel(const uint32_t* __restrict__ send_count, uint32_t nb1, uint32_t cap_seg, PeerDest dest,
-                                                             uint64_t seg_count_off) {
-  const uint32_t d = blockIdx.x * 256 + threadIdx.x;
-  if (d >= nb1) return;
-  const uint32_t owner = d >> dest.bucket_shift, local = d & ((1u << dest.bucket_shift) - 1u);
-  reinterpret_cast<uint32_t*>(dest.base[owner] + seg_count_off)[local * dest.world + dest.src] = min(send_count[d], cap_seg);
+// The home rank applies the answers about its positions: it reads the list every owner kept for it
+// (coalesced loads over NVLink) and updates its own words.  answer = (position << 32) | first position
+// (a later occurrence) or | 0xffffffff (a first occurrence whose key occurred again).
+__global__ void __launch_bounds__(256)
+apply_answers_kernel(PeerHome home, uint32_t world, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits) {
+  const uint32_t owner = blockIdx.y;
+  const uint32_t count = min(*reinterpret_cast<const volatile uint32_t*>(home.base[owner] + home.ans_count_off + 4ull * home.self), home.ans_cap);
+  const unsigned long long* list = reinterpret_cast<const unsigned long long*>(home.base[owner] + home.ans_off) + (uint64_t)home.self * home.ans_cap;
+  const uint32_t mask = (1u << home.log2_positions) - 1u;
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < count; i += gridDim.x * 256) {
+    const unsigned long long a = __ldcs(list + i);
+    const uint32_t p = (uint32_t)(a >> 32) & mask, fp = (uint32_t)a;
+    if (fp == 0xffffffffu) {
+      atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
+    } else {
+      atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
+      atomicOr(aux + p, fp);
+    }
+  }
+  (void)world;
 }
 
 // local number of first occurrences = sum of the chunk totals
@@ -410,10 +423,12 @@ struct Shard : Ctx {
   char* peers[STB_MAX_RANKS] = {};
   bool shared = false;
   uint64_t off_ptr[2] = {}, off_aux = 0, off_first[2] = {}, off_multi[2] = {}, off_seg_keys = 0, off_seg_pos = 0, off_seg_count = 0;
+  uint64_t off_ans = 0, off_ans_count = 0, ans_records = 0;
 
   // local scratch and results
-  DevBuf<uint32_t> dminpos, dids, leaf_bits, tilecnt, send_count, count2, scalars, totals_all;
+  DevBuf<uint32_t> dminpos, dids, leaf_bits, tilecnt, count2, scalars, totals_all;
   BucketWorkspace ws;
+  DevBuf<char> staging;                // host input lands here
   DevBuf<unsigned long long> leaves;   // the whole leaf table (every rank computes it; rank 0's is the tree's)
   std::vector<DevBuf<uint2>> slices;   // this rank's id range of every sharded node layer
   std::vector<uint32_t> h_totals;      // [level][rank] unique counts (level 0 = leaves: [0] only), after a build
@@ -455,12 +470,15 @@ int ensure_arena(Shard& s) {
     s.off_first[i] = carve(ceil_div(P, LVL_TILE) * (LVL_TILE / 8));
     s.off_multi[i] = carve(ceil_div(P, LVL_TILE) * (LVL_TILE / 8));
   }
-  // segments: everything the world can send to this rank's buckets at the largest level
-  // (per source and bucket: mean P / 2^b1 records, with head-room; at most 2^9 x world buckets)
-  const uint64_t seg_records = P + P * s.opt.bucket_slack_permille / 1000 + 512ull * STB_MAX_RANKS * 512;
+  // this rank's first-pass buckets at the largest level (mean P / 2^b1 records each, with head-room; at most
+  // 2^9 buckets), and the answers it keeps for every home rank
+  const uint64_t seg_records = P + P * s.opt.bucket_slack_permille / 1000 + 512ull * 512;
   s.off_seg_keys = carve(seg_records * 8);
   s.off_seg_pos = carve(seg_records * 4);
-  s.off_seg_count = carve(512ull * STB_MAX_RANKS * 4);
+  s.off_seg_count = carve(512ull * 4);
+  s.ans_records = 2 * P / (uint64_t)s.comm->world + 65536;  // per home rank
+  s.off_ans = carve(s.ans_records * 8 * (uint64_t)s.comm->world);
+  s.off_ans_count = carve(STB_MAX_RANKS * 4);
   s.arena_bytes = off;
   STB_CUDA(s, cudaMalloc(&s.arena, s.arena_bytes));
   s.arena_shard = s.shard;
@@ -487,11 +505,14 @@ ShardBuckets level_buckets(const Shard& s, uint64_t n_total, uint64_t P, int lev
   sb.dest.world = (uint32_t)s.comm->world;
   sb.dest.keys_off = s.off_seg_keys;
   sb.dest.pos_off = s.off_seg_pos;
-  sb.home.aux_off = s.off_aux;
-  sb.home.first_off = s.off_first[level_parity];
-  sb.home.multi_off = s.off_multi[level_parity];
+  sb.dest.count_off = s.off_seg_count;
+  sb.home.ans_off = s.off_ans;
+  sb.home.ans_count_off = s.off_ans_count;
+  sb.home.ans_cap = (uint32_t)std::min<uint64_t>(s.ans_records, 0xffffffffull);
+  sb.home.self = (uint32_t)s.comm->rank;
   sb.home.log2_positions = (uint32_t)log2_exact(P);
   for (int r = 0; r < s.comm->world; ++r) sb.dest.base[r] = sb.home.base[r] = s.peers[r];
+  (void)level_parity;
   (void)out_ptr;
   return sb;
 }
@@ -523,7 +544,6 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     const uint64_t tiles = ceil_div(n0, LVL_TILE);
     STB_CUDA(s, s.tilecnt.ensure(tiles + tiles / CHUNK_TILES + 2, st));
   }
-  STB_CUDA(s, s.send_count.ensure(512, st));
   STB_CUDA(s, s.scalars.ensure(8, st));  // [0] local total, [1] id base, [2] level total, [3] overflow
   STB_CUDA(s, s.totals_all.ensure((uint64_t)world * 48 + 48, st));
   STB_CUDA(s, s.leaves.ensure(std::min<uint64_t>(n0, canon_entries) + 1, st));
@@ -586,23 +606,26 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     const uint32_t* child_multi = (j > 0 && s.opt.child_filter) ? reinterpret_cast<uint32_t*>(s.arena + s.off_multi[par ^ 1]) : nullptr;
     const ShardBuckets sb = level_buckets(s, n_total, P, par, cur_which ^ 1);
     const uint32_t nb1 = 1u << sb.b1, local1 = 1u << sb.dest.bucket_shift;
-    if ((uint64_t)local1 * world * sb.cap_seg > (s.off_seg_pos - s.off_seg_keys) / 8)
-      return s.fail(STB_ERR_TOO_LARGE, "sharded build: segment arena too small for this level (raise bucket_slack_permille)");
+    if ((uint64_t)nb1 * sb.cap_seg > (s.off_seg_pos - s.off_seg_keys) / 8)
+      return s.fail(STB_ERR_TOO_LARGE, "sharded build: bucket arena too small for this level (raise bucket_slack_permille)");
     const uint64_t words = ceil_div(std::max<uint64_t>(P, 1), LVL_TILE) * (LVL_TILE / 32);
+    unsigned long long* seg_keys = reinterpret_cast<unsigned long long*>(s.arena + s.off_seg_keys);
+    uint32_t* seg_pos = reinterpret_cast<uint32_t*>(s.arena + s.off_seg_pos);
+    uint32_t* seg_count = reinterpret_cast<uint32_t*>(s.arena + s.off_seg_count);
     STB_CUDA(s, cudaMemsetAsync(first_bits, 0, words * 4, st));
     STB_CUDA(s, cudaMemsetAsync(multi_bits, 0, words * 4, st));
-    STB_CUDA(s, cudaMemsetAsync(s.send_count.ptr, 0, 512 * 4, st));
+    STB_CUDA(s, cudaMemsetAsync(seg_count, 0, 512 * 4, st));
+    STB_CUDA(s, cudaMemsetAsync(s.arena + s.off_ans_count, 0, STB_MAX_RANKS * 4, st));
     STB_TRY(shard_partition(s, sb, ptr_cur, (uint32_t)n_cur_local, (uint32_t)n_next_local, (uint32_t)lo, child_first, child_multi, aux, first_bits,
-                            s.send_count.ptr, s.scalars.ptr + 3));
-    {
-      Launch l(s, "shard_publish");
-      publish_counts_kernel<<<(nb1 + 255) / 256, 256, 0, st>>>(s.send_count.ptr, nb1, sb.cap_seg, sb.dest, s.off_seg_count);
-    }
-    STB_TRY(comm.barrier(s));
+                            seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
+    STB_TRY(comm.barrier(s));  // every rank's buckets are complete: the owners pull them
     STB_CUDA(s, s.count2.ensure((uint64_t)local1 << sb.b2, st));
-    STB_TRY(shard_dedup(s, sb, s.ws, reinterpret_cast<unsigned long long*>(s.arena + s.off_seg_keys), reinterpret_cast<uint32_t*>(s.arena + s.off_seg_pos),
-                        reinterpret_cast<uint32_t*>(s.arena + s.off_seg_count), s.count2.ptr, s.scalars.ptr + 3));
-    STB_TRY(comm.barrier(s));
+    STB_TRY(shard_dedup(s, sb, s.ws, s.count2.ptr, s.scalars.ptr + 3));
+    STB_TRY(comm.barrier(s));  // every owner's answer lists are complete: the home ranks pull them
+    {
+      Launch l(s, "shard_apply");
+      apply_answers_kernel<<<dim3(148, world), 256, 0, st>>>(sb.home, (uint32_t)world, aux, first_bits, multi_bits);
+    }
     // ids: local counts -> the world's totals -> this rank's base
     const uint32_t tiles = (uint32_t)ceil_div(n_next_local, LVL_TILE), chunks = tiles / CHUNK_TILES + 1;
     uint32_t* chunkcnt = s.tilecnt.ptr + tiles;
@@ -815,12 +838,12 @@ int stb_shard_build_from_body(stb_shard* s, const char* body_local, uint64_t n_b
   uint64_t first = 0, count = 0;
   STB_TRY(stb_shard_range(s, n_bases_total, &first, &count));
   const char* d = body_local;
-  DevBuf<char> hold;
   if (memory == STB_HOST || (reinterpret_cast<uintptr_t>(body_local) & 15u)) {
-    STB_CUDA(*s, hold.alloc(count + 16, s->stream));
+    // the handle's grow-only staging buffer: no device allocation per call in steady state
+    STB_CUDA(*s, s->staging.ensure(count + 16, s->stream));
     if (count)
-      STB_CUDA(*s, cudaMemcpyAsync(hold.ptr, body_local, count, memory == STB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
-    d = hold.ptr;
+      STB_CUDA(*s, cudaMemcpyAsync(s->staging.ptr, body_local, count, memory == STB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+    d = s->staging.ptr;
   }
   return shard_build(*s, d, n_bases_total);
 }
