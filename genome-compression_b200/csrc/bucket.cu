@@ -96,6 +96,18 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
 
   unsigned long long key[PT_ITEMS];
   uint32_t pos[PT_ITEMS], dr[PT_ITEMS];
+  if (!FROM_CHILDREN) {
+    // all of a thread's loads are issued before the first one is used: a segment pulled over NVLink
+    // answers after a few microseconds, and only bytes in flight hide that
+#pragma unroll
+    for (int it = 0; it < PT_ITEMS; ++it) {
+      const uint32_t i = first + it * PT_THREADS + tid;
+      if (i < count) {
+        key[it] = __ldcs(in_keys + in_base + i);
+        pos[it] = __ldcs(in_pos + in_base + i);
+      }
+    }
+  }
 #pragma unroll
   for (int it = 0; it < PT_ITEMS; ++it) {
     const uint32_t i = first + it * PT_THREADS + tid;
@@ -124,9 +136,6 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
         key[it] = pair_key(cl, cr);
         aux[i] = f;  // flags at bits 29..31; the dedup kernel ORs the first occurrence's position below them
       }
-    } else if (valid) {
-      key[it] = __ldcs(in_keys + in_base + i);
-      pos[it] = __ldcs(in_pos + in_base + i);
     }
     if (valid) {
       const uint32_t d = (uint32_t)(bucket_hash(key[it]) >> shift) & (nb - 1u);

@@ -492,6 +492,8 @@ struct Scratch {
   DevBuf<Slot> stream_slots;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_events;
+  DevBuf<char> stream_body;  // streaming FASTA ingest: the extracted body
+  FastaStream fasta;
   int coop_grid = 0;  // CTAs of the cooperative middle launch (0 = not yet asked)
   ~Scratch() {
     for (auto e : chunk_events) cudaEventDestroy(e);
@@ -830,21 +832,29 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
 // the next one is still on the PCIe bus; the scan of each level simply continues from the running
 // total.  Only the last chunk's work and the small top of the tree remain after the copy ends.
 // (No singleton filter here: whether a child occurs again is not known before the last chunk.)
-int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
-  const int S = t.S;
-  const uint64_t n0 = body_len / (uint64_t)S;
-  const int chunk_log2 = (int)t.opt.stream_chunk_log2;
-  const uint64_t min_chunks = t.opt.stream_min_chunks;
-  if (chunk_log2 < 12 || chunk_log2 > 30) return -1;
-  const uint64_t C = 1ull << chunk_log2;
-  if (S > 12 || n0 < min_chunks * C || n0 >= (1ull << 30)) return -1;
-  const int Lc = chunk_log2 - 11;  // chunked node levels: a chunk still holds 2048 positions at the last one
-  cudaStream_t st = t.stream;
-  t.clear();
-  Scratch& sc = workspace_of(t);
+struct StreamPlan {
+  int S = 12, Lc = 0;
+  uint64_t C = 0;       // leaves per chunk
+  uint64_t bound = 0;   // upper bound of the leaf count (allocation, table capacities, placement scaling)
+  std::vector<uint64_t> n, ptr_off, bit_off, slot_off;  // per chunked level, from `bound`
+  std::vector<uint32_t> serial;
+};
 
-  std::vector<uint64_t> n(Lc + 1), ptr_off(Lc + 2, 0), bit_off(Lc + 2, 0), slot_off(Lc + 2, 0);
-  n[0] = n0;
+// Allocations, clears and the per-level layout for a text of at most `bound` leaves.
+int stream_begin(Tree& t, Scratch& sc, StreamPlan& sp, uint64_t bound) {
+  const int S = t.S;
+  cudaStream_t st = t.stream;
+  sp.S = S;
+  sp.bound = bound;
+  const int chunk_log2 = (int)t.opt.stream_chunk_log2;
+  sp.C = 1ull << chunk_log2;
+  const int Lc = sp.Lc = chunk_log2 - 11;  // chunked node levels: a chunk still holds 2048 positions at the last one
+  auto &n = sp.n, &ptr_off = sp.ptr_off, &bit_off = sp.bit_off, &slot_off = sp.slot_off;
+  n.assign(Lc + 1, 0);
+  ptr_off.assign(Lc + 2, 0);
+  bit_off.assign(Lc + 2, 0);
+  slot_off.assign(Lc + 2, 0);
+  n[0] = bound;
   for (int j = 1; j <= Lc; ++j) n[j] = ceil_div(n[j - 1], 2);
   for (int j = 0; j <= Lc; ++j) {
     const uint64_t blocks = ceil_div(n[j], LVL_TILE);
@@ -853,17 +863,15 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
     slot_off[j + 1] = slot_off[j] + (j == 0 ? 0 : (uint64_t)table_cap(n[j]) + 1);
   }
   const uint64_t direct_entries = 1ull << (2 * S);
-  const uint64_t n_top = n[Lc];
-  STB_CUDA(t, t.staging.ensure(n0 * (uint64_t)S + 16, st));
   STB_CUDA(t, sc.ptr_arena.ensure(ptr_off[Lc + 1], st));
   STB_CUDA(t, sc.bit_arena.ensure(bit_off[Lc + 1], st));
   STB_CUDA(t, sc.run_totals.ensure(2 * (Lc + 1), st));
-  STB_CUDA(t, sc.tilecnt.ensure(2 * ceil_div(C, LVL_TILE) + 4, st));  // one chunk's tiles at a time (the node workspace below may ask for more)
+  STB_CUDA(t, sc.tilecnt.ensure(2 * ceil_div(sp.C, LVL_TILE) + 4, st));  // one chunk's tiles at a time (the node workspace below may ask for more)
   STB_CUDA(t, sc.level_sizes.ensure(Lc + 2, st));
   STB_CUDA(t, sc.flags.ensure(1, st));
   STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
   STB_CUDA(t, sc.dids.ensure(direct_entries, st));
-  STB_TRY(reserve_node_workspace(t, sc, n_top));  // the top of the tree, as in the one-shot build
+  STB_TRY(reserve_node_workspace(t, sc, n[Lc]));  // the top of the tree, as in the one-shot build
   {
     bool grew = false;
     STB_CUDA(t, sc.stream_slots.ensure(slot_off[Lc + 1], st, &grew));
@@ -886,91 +894,181 @@ int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
     STB_CUDA(t, cudaMemcpyAsync(sc.level_sizes.ptr, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, st));
     STB_CUDA(t, cudaStreamSynchronize(st));  // `sizes` and `init` are stack memory
   }
-  STB_CUDA(t, t.leaves.alloc(std::min<uint64_t>(n0, direct_entries), st));
+  STB_CUDA(t, t.leaves.alloc(std::min<uint64_t>(bound, direct_entries), st));
   t.layers.clear();
   for (int j = 1; j <= Lc; ++j) {
     t.layers.emplace_back();
     STB_CUDA(t, t.layers.back().nodes.alloc(n[j], st));
   }
-  std::vector<uint32_t> serial(Lc + 1, 0);
-  for (int j = 1; j <= Lc; ++j) serial[j] = ++sc.stream_serial;
+  sp.serial.assign(Lc + 1, 0);
+  for (int j = 1; j <= Lc; ++j) sp.serial[j] = ++sc.stream_serial;
+  return STB_OK;
+}
 
-  // all chunk copies are queued at once on their own stream; compute waits chunk by chunk
+// Leaves [c * C, c * C + cnt) of the body at `body` (device, the whole body's first byte) through the
+// chunked levels.  `n0` is the true leaf count when this is the last chunk (the ragged right edge is
+// only ever touched then), else the bound.
+int stream_chunk(Tree& t, Scratch& sc, const StreamPlan& sp, const char* body, uint64_t c, uint64_t cnt, uint64_t n0) {
+  const int S = sp.S, Lc = sp.Lc;
+  cudaStream_t st = t.stream;
+  uint32_t* const ptrs = sc.ptr_arena.ptr;
+  uint32_t* const bits = sc.bit_arena.ptr;
+  LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
+  leaf_tab.first_bits = bits;
+  const uint64_t first = c * sp.C;
+  if (S == 12) launch_leaf_text<12, true>(t, body + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
+  else launch_leaf_text<0, true>(t, body + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
+  for (int j = 0; j <= Lc; ++j) {
+    const uint64_t begin = first >> j, end = ceil_div(first + cnt, 1ull << j);
+    const uint64_t n_here = ceil_div(n0, 1ull << j), n_below = j ? ceil_div(n0, 1ull << (j - 1)) : 0;
+    const uint32_t fb = (uint32_t)(begin / LVL_TILE), nbk = (uint32_t)ceil_div(end - begin, LVL_TILE);
+    uint32_t* lvl_ptr = ptrs + sp.ptr_off[j];
+    uint32_t* lvl_bits = bits + sp.bit_off[j];
+    // running total of the level: read from one copy, the new total goes to the other
+    const uint32_t* carry = sc.run_totals.ptr + (c & 1) * (Lc + 1) + j;
+    uint32_t* total = sc.run_totals.ptr + ((c + 1) & 1) * (Lc + 1) + j;
+    uint32_t* tilecnt = sc.tilecnt.ptr;
+    uint32_t* chunkcnt = tilecnt + nbk;
+    LevelTable tab = leaf_tab;
+    if (j > 0) {
+      tab = LevelTable{sc.stream_slots.ptr + sp.slot_off[j], nullptr, nullptr, table_cap(sp.n[j])};
+      tab.first_bits = lvl_bits;
+      Launch l(t, "node_insert");
+      // placement by child id above the first node layer; child ids are bounded by the child level's size
+      const uint32_t* child_unique = (j > 1 && t.opt.locality) ? sc.level_sizes.ptr + (j - 1) : nullptr;
+      node_insert_kernel<<<nbk, LVL_THREADS, 0, st>>>(ptrs + sp.ptr_off[j - 1], (uint32_t)n_below, (uint32_t)end, tab, lvl_ptr, child_unique,
+                                                       sp.serial[j], nullptr, nullptr, fb, nullptr);
+    }
+    STB_CUDA(t, cudaMemsetAsync(chunkcnt, 0, (nbk / CHUNK_TILES + 1) * 4, st));
+    {
+      Launch l(t, "count_firsts");
+      count_kernel<<<(unsigned)ceil_div((uint64_t)nbk * 32, 256), 256, 0, st>>>(lvl_bits, fb, nbk, tilecnt, chunkcnt);
+    }
+    {
+      Launch l(t, "assign_ids");
+      if (j == 0)
+        assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n_here, tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total, t.leaves.ptr, S,
+                                                                     nullptr, 0u);
+      else
+        assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total,
+                                                              t.layers[j - 1].nodes.ptr, S, ptrs + sp.ptr_off[j - 1], (uint32_t)n_below);
+    }
+    {
+      Launch l(t, "resolve_ids");
+      if (j == 0)
+        resolve_kernel<RESOLVE_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)std::min<uint64_t>(n_here, first + cnt), tab, lvl_bits, fb,
+                                                                    nullptr, nullptr);
+      else
+        resolve_kernel<RESOLVE_TABLE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)end, tab, lvl_bits, fb, nullptr, nullptr);
+    }
+  }
+  return STB_OK;
+}
+
+// The top of the tree: everything above the last chunked level, as in the one-shot build.
+int stream_finish(Tree& t, Scratch& sc, const StreamPlan& sp, uint64_t n0, uint64_t chunks) {
+  const int Lc = sp.Lc;
+  cudaStream_t st = t.stream;
+  const uint64_t n_top = ceil_div(n0, 1ull << Lc);
+  STB_CUDA(t, cudaMemcpyAsync(sc.counts.ptr, sc.run_totals.ptr + (chunks & 1) * (Lc + 1), (Lc + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, sc.ptr_arena.ptr + sp.ptr_off[Lc], n_top * 4, cudaMemcpyDeviceToDevice, st));
+  int more = 0;
+  uint32_t* cur = nullptr;
+  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n_top, sc.counts.ptr + 1 + Lc, &more, &cur));
+  return finish_build(t, sc, n0, Lc + more, cur, true);
+}
+
+int ensure_copy_stream(Tree& t, Scratch& sc, uint64_t events) {
   if (!sc.copy_stream) STB_CUDA(t, cudaStreamCreateWithFlags(&sc.copy_stream, cudaStreamNonBlocking));
-  const uint64_t chunks = ceil_div(n0, C);
-  while (sc.chunk_events.size() < chunks) {
+  while (sc.chunk_events.size() < events) {
     cudaEvent_t e;
     STB_CUDA(t, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     sc.chunk_events.push_back(e);
   }
+  return STB_OK;
+}
+
+bool streaming_applies(const Tree& t, uint64_t n0_bound) {
+  const uint64_t log2c = t.opt.stream_chunk_log2;
+  if (log2c < 12 || log2c > 30 || t.S > 12) return false;
+  return n0_bound >= t.opt.stream_min_chunks * (1ull << log2c) && n0_bound < (1ull << 30);
+}
+
+int build_streaming(Tree& t, const char* h_body, uint64_t body_len) {
+  const int S = t.S;
+  const uint64_t n0 = body_len / (uint64_t)S;
+  if (!streaming_applies(t, n0)) return -1;
+  cudaStream_t st = t.stream;
+  t.clear();
+  Scratch& sc = workspace_of(t);
+  StreamPlan sp;
+  STB_CUDA(t, t.staging.ensure(n0 * (uint64_t)S + 16, st));
+  STB_TRY(stream_begin(t, sc, sp, n0));
+  const uint64_t C = sp.C, chunks = ceil_div(n0, C);
+  // all chunk copies are queued at once on their own stream; compute waits chunk by chunk
+  STB_TRY(ensure_copy_stream(t, sc, chunks));
   char* text = t.staging.ptr;
   for (uint64_t c = 0; c < chunks; ++c) {
     const uint64_t first = c * C, cnt = std::min<uint64_t>(C, n0 - first);
     STB_CUDA(t, cudaMemcpyAsync(text + first * S, h_body + first * S, cnt * S, cudaMemcpyHostToDevice, sc.copy_stream));
     STB_CUDA(t, cudaEventRecord(sc.chunk_events[c], sc.copy_stream));
   }
-
-  uint32_t* const ptrs = sc.ptr_arena.ptr;
-  uint32_t* const bits = sc.bit_arena.ptr;
-  LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
-  leaf_tab.first_bits = bits;
   for (uint64_t c = 0; c < chunks; ++c) {
-    const uint64_t first = c * C, cnt = std::min<uint64_t>(C, n0 - first);
     STB_CUDA(t, cudaStreamWaitEvent(st, sc.chunk_events[c], 0));
-    // leaf level of this chunk
-    if (S == 12) launch_leaf_text<12, true>(t, text + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
-    else launch_leaf_text<0, true>(t, text + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
-    for (int j = 0; j <= Lc; ++j) {
-      const uint64_t begin = first >> j, end = ceil_div(first + cnt, 1ull << j);
-      const uint32_t fb = (uint32_t)(begin / LVL_TILE), nbk = (uint32_t)ceil_div(end - begin, LVL_TILE);
-      uint32_t* lvl_ptr = ptrs + ptr_off[j];
-      uint32_t* lvl_bits = bits + bit_off[j];
-      // running total of the level: read from one copy, the new total goes to the other
-      const uint32_t* carry = sc.run_totals.ptr + (c & 1) * (Lc + 1) + j;
-      uint32_t* total = sc.run_totals.ptr + ((c + 1) & 1) * (Lc + 1) + j;
-      uint32_t* tilecnt = sc.tilecnt.ptr;
-      uint32_t* chunkcnt = tilecnt + nbk;
-      LevelTable tab = leaf_tab;
-      if (j > 0) {
-        tab = LevelTable{sc.stream_slots.ptr + slot_off[j], nullptr, nullptr, table_cap(n[j])};
-        tab.first_bits = lvl_bits;
-        Launch l(t, "node_insert");
-        // placement by child id above the first node layer; child ids are bounded by the child level's size
-        const uint32_t* child_unique = (j > 1 && t.opt.locality) ? sc.level_sizes.ptr + (j - 1) : nullptr;
-        node_insert_kernel<<<nbk, LVL_THREADS, 0, st>>>(ptrs + ptr_off[j - 1], (uint32_t)n[j - 1], (uint32_t)end, tab, lvl_ptr, child_unique,
-                                                         serial[j], nullptr, nullptr, fb, nullptr);
-      }
-      STB_CUDA(t, cudaMemsetAsync(chunkcnt, 0, (nbk / CHUNK_TILES + 1) * 4, st));
-      {
-        Launch l(t, "count_firsts");
-        count_kernel<<<(unsigned)ceil_div((uint64_t)nbk * 32, 256), 256, 0, st>>>(lvl_bits, fb, nbk, tilecnt, chunkcnt);
-      }
-      {
-        Launch l(t, "assign_ids");
-        if (j == 0)
-          assign_kernel<MODE_LEAF_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)n[0], tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total, t.leaves.ptr, S,
-                                                                       nullptr, 0u);
-        else
-          assign_kernel<MODE_NODE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, (uint32_t)end, tab, lvl_bits, tilecnt, chunkcnt, fb, carry, total,
-                                                                t.layers[j - 1].nodes.ptr, S, ptrs + ptr_off[j - 1], (uint32_t)n[j - 1]);
-      }
-      {
-        Launch l(t, "resolve_ids");
-        if (j == 0)
-          resolve_kernel<RESOLVE_DIRECT><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)std::min<uint64_t>(n[0], first + cnt), tab, lvl_bits, fb,
-                                                                      nullptr, nullptr);
-        else
-          resolve_kernel<RESOLVE_TABLE><<<nbk, LVL_THREADS, 0, st>>>(lvl_ptr, lvl_ptr, (uint32_t)end, tab, lvl_bits, fb, nullptr, nullptr);
-      }
+    STB_TRY(stream_chunk(t, sc, sp, text, c, std::min<uint64_t>(C, n0 - c * C), n0));
+  }
+  return stream_finish(t, sc, sp, n0, chunks);
+}
+
+// The same for FASTA text with headers and line breaks (fasta_reader::load_buffer, src/fasta_reader.cpp:40-68,
+// which overlaps reading with building through its loader thread, :92-106): the text is copied in
+// chunks, every chunk is extracted as soon as it has arrived (the line automaton's state is carried
+// on the device, ingest.cu), and every time the body has grown by a whole leaf chunk that chunk is built.
+// The host reads one number per text chunk: how long the body has become.
+int build_streaming_fasta(Tree& t, const char* h_text, uint64_t len) {
+  const int S = t.S;
+  const uint64_t bound = len / (uint64_t)S;
+  if (!streaming_applies(t, bound)) return -1;
+  cudaStream_t st = t.stream;
+  t.clear();
+  Scratch& sc = workspace_of(t);
+  StreamPlan sp;
+  STB_CUDA(t, t.staging.ensure(len + 16, st));
+  STB_CUDA(t, sc.stream_body.ensure(len + 64, st));
+  STB_TRY(stream_begin(t, sc, sp, bound));
+  const uint64_t C = sp.C;
+  const uint64_t text_chunk = std::max<uint64_t>(FASTA_STREAM_ALIGN, (C * S / 2) & ~(FASTA_STREAM_ALIGN - 1));
+  const uint64_t text_chunks = ceil_div(len, text_chunk);
+  STB_TRY(ensure_copy_stream(t, sc, text_chunks));
+  STB_TRY(fasta_stream_begin(t, sc.fasta, text_chunk));
+  char* text = t.staging.ptr;
+  char* body = sc.stream_body.ptr;
+  for (uint64_t i = 0; i < text_chunks; ++i) {
+    const uint64_t first = i * text_chunk, cnt = std::min<uint64_t>(text_chunk, len - first);
+    STB_CUDA(t, cudaMemcpyAsync(text + first, h_text + first, cnt, cudaMemcpyHostToDevice, sc.copy_stream));
+    STB_CUDA(t, cudaEventRecord(sc.chunk_events[i], sc.copy_stream));
+  }
+  uint64_t built = 0;  // leaf chunks already built
+  uint64_t body_len = 0;
+  for (uint64_t i = 0; i < text_chunks; ++i) {
+    const uint64_t first = i * text_chunk, cnt = std::min<uint64_t>(text_chunk, len - first);
+    STB_CUDA(t, cudaStreamWaitEvent(st, sc.chunk_events[i], 0));
+    STB_TRY(fasta_stream_chunk(t, sc.fasta, text, first, cnt, body));
+    STB_TRY(fasta_stream_body_len(t, sc.fasta, &body_len));
+    // whole leaf chunks that are complete and are certainly not the last one
+    while ((built + 1) * C * S <= body_len && (i + 1 < text_chunks || (built + 1) * C < body_len / S)) {
+      STB_TRY(stream_chunk(t, sc, sp, body, built, C, bound));
+      ++built;
     }
   }
-  STB_CUDA(t, cudaMemcpyAsync(sc.counts.ptr, sc.run_totals.ptr + (chunks & 1) * (Lc + 1), (Lc + 1) * 4, cudaMemcpyDeviceToDevice, st));
-  // the top of the tree: everything above the last chunked level, as in the one-shot build
-  STB_CUDA(t, cudaMemcpyAsync(sc.ptr_a.ptr, ptrs + ptr_off[Lc], n_top * 4, cudaMemcpyDeviceToDevice, st));
-  int more = 0;
-  uint32_t* cur = nullptr;
-  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n_top, sc.counts.ptr + 1 + Lc, &more, &cur));
-  return finish_build(t, sc, n0, Lc + more, cur, true);
+  const uint64_t n0 = body_len / (uint64_t)S;
+  if (n0 == 0) return t.fail(STB_ERR_EMPTY, "input holds fewer than dna_size bases");
+  if (built == 0) return build_from_body(t, body, body_len);  // hardly any body: not worth (or not valid) chunking
+  if (n0 > built * C) {
+    STB_TRY(stream_chunk(t, sc, sp, body, built, n0 - built * C, n0));
+    ++built;
+  }
+  return stream_finish(t, sc, sp, n0, built);
 }
 
 int build_dispatch(Tree& t, const LeafInput& in, uint64_t n0) {
@@ -1055,6 +1153,7 @@ int build_from_body(Tree& t, const char* d_body, uint64_t body_len) {
 // Host text: overlap the copy with the build when the input is large enough; -1 = not applicable
 // (small input, dna_size > 12, or non-ACGT symbols), the caller copies and builds in one shot.
 int build_from_host_body(Tree& t, const char* h_body, uint64_t body_len) { return build_streaming(t, h_body, body_len); }
+int build_from_host_fasta(Tree& t, const char* h_text, uint64_t len) { return build_streaming_fasta(t, h_text, len); }
 
 int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n) {
   LeafInput in;

@@ -260,10 +260,14 @@ int stb_build_from_fasta(stb_tree* tree, const char* text, uint64_t len, int mem
   if (!tree || (!text && len) || !valid_memory(memory)) return STB_ERR_INVALID_ARG;
   STB_TRY(use_device(tree));
   Tree& t = *tree;
+  if (len == 0) return t.fail(STB_ERR_EMPTY, "input holds fewer than dna_size bases");
+  if (memory == STB_HOST) {  // large host inputs: extract and build chunk by chunk behind the copy
+    const int s = build_from_host_fasta(t, text, len);
+    if (s != -1) return s;
+  }
   DevBuf<char> hold;
   const char* d = nullptr;
   STB_TRY(to_device(t, text, len, memory, hold, &d));
-  if (len == 0) return t.fail(STB_ERR_EMPTY, "input holds fewer than dna_size bases");
   DevBuf<uint32_t> flag;
   STB_CUDA(t, flag.alloc(1, t.stream));
   STB_CUDA(t, cudaMemsetAsync(flag.ptr, 0, 4, t.stream));

@@ -150,7 +150,7 @@ template <int PHASE>
 __global__ void __launch_bounds__(FX_THREADS)
 fasta_tile_kernel(const char* __restrict__ text, uint64_t len, RunSum* __restrict__ run_sums,
                   const RunSum* __restrict__ run_carry, TileSum* __restrict__ tile_sums,
-                  const FxCarry* __restrict__ carry, char* __restrict__ body) {
+                  const FxCarry* __restrict__ carry, char* __restrict__ body, const char* text_begin) {
   __shared__ RunSum sm_run[FX_THREADS / 32];
   __shared__ SkipSum sm_skip[FX_THREADS / 32];
   __shared__ U32Sum sm_cnt[FX_THREADS / 32];
@@ -166,7 +166,8 @@ fasta_tile_kernel(const char* __restrict__ text, uint64_t len, RunSum* __restric
   if (PHASE == 2) in_skip0 = in_skip1 = carry[blockIdx.x].in_skip;
   uint32_t tile_has_ls = 0, tile_last_skip = 0, tile_cnt0 = 0, tile_cnt1 = 0;
   uint64_t out_off = PHASE == 2 ? carry[blockIdx.x].out_off : 0;
-  uint8_t prev_sub_last = tile_base == 0 ? (uint8_t)'\n' : (uint8_t)text[tile_base - 1];
+  // `text` may be a later chunk of a text that begins at text_begin: the byte before it is then real
+  uint8_t prev_sub_last = (text + tile_base == text_begin) ? (uint8_t)'\n' : (uint8_t)text[(int64_t)tile_base - 1];
 
   for (int sub = 0; sub < FX_SUBS_PER_TILE; ++sub) {
     const uint64_t sub_base = tile_base + (uint64_t)sub * FX_SUB;
@@ -314,10 +315,18 @@ fasta_tile_kernel(const char* __restrict__ text, uint64_t len, RunSum* __restric
 // Single-thread-per-element would be enough (<= ~50K tiles), but keep it parallel:
 // exclusive scans over tiles with the two operators, done by one CTA sequentially in
 // chunks of 256.
+// What the automaton carries from one chunk of a text to the next (streaming ingest).
+struct FxStream {
+  RunSum run;        // hb-run state at the end of the text seen so far
+  uint32_t in_skip;  // is the line the text ends in a skipped one
+  uint32_t pad;
+  unsigned long long out_off;  // body bytes produced so far
+};
+
 __global__ void __launch_bounds__(FX_THREADS) fasta_scan_run_kernel(const RunSum* __restrict__ sums, uint32_t n,
-                                                                    RunSum* __restrict__ carry) {
+                                                                    RunSum* __restrict__ carry, FxStream* __restrict__ stream) {
   __shared__ RunSum sm[FX_THREADS / 32];
-  RunSum state{1u, 0u};
+  RunSum state = stream ? stream->run : RunSum{1u, 0u};
   for (uint32_t base = 0; base < n; base += FX_THREADS) {
     const uint32_t i = base + threadIdx.x;
     const RunSum v = i < n ? sums[i] : RunSum{1u, 0u};
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(FX_THREADS) fasta_scan_run_kernel(const RunSum
     if (i < n) carry[i] = run_compose(state, before);
     state = run_compose(state, total);
   }
+  if (stream && threadIdx.x == 0) stream->run = state;  // the skip scan below reads run_carry[], not this
 }
 
 struct ScanB {
@@ -349,10 +359,14 @@ __device__ __forceinline__ ScanB scanb_compose(ScanB a, ScanB b) {
 
 __global__ void __launch_bounds__(FX_THREADS)
 fasta_scan_skip_kernel(const TileSum* __restrict__ sums, const RunSum* __restrict__ run_carry, uint32_t n,
-                       FxCarry* __restrict__ carry, unsigned long long* __restrict__ body_len) {
+                       FxCarry* __restrict__ carry, unsigned long long* __restrict__ body_len, FxStream* __restrict__ stream) {
   __shared__ ScanB sm[FX_THREADS / 32];
   const ScanB ident{0u, 0u, 0u, 0u, 0u, 0u};
   ScanB state = ident;  // the file is entered in skip state 0
+  if (stream) {  // a later chunk is entered in the state, and at the body offset, the text so far ended with
+    const unsigned long long o = stream->out_off;
+    state = ScanB{1u, stream->in_skip, (uint32_t)o, (uint32_t)(o >> 32), (uint32_t)o, (uint32_t)(o >> 32)};
+  }
   for (uint32_t base = 0; base < n; base += FX_THREADS) {
     const uint32_t i = base + threadIdx.x;
     ScanB v = ident;
@@ -372,7 +386,13 @@ fasta_scan_skip_kernel(const TileSum* __restrict__ sums, const RunSum* __restric
     }
     state = scanb_compose(state, total);
   }
-  if (threadIdx.x == 0) *body_len = u64_of(state.cnt0_lo, state.cnt0_hi);
+  if (threadIdx.x == 0) {
+    *body_len = u64_of(state.cnt0_lo, state.cnt0_hi);
+    if (stream) {
+      stream->in_skip = state.has_ls ? state.last_skip : 0u;
+      stream->out_off = u64_of(state.cnt0_lo, state.cnt0_hi);
+    }
+  }
 }
 
 int fasta_extract_body(Ctx& ctx, const char* d_text, uint64_t len, DevBuf<char>& body, uint64_t* body_len) {
@@ -391,26 +411,93 @@ int fasta_extract_body(Ctx& ctx, const char* d_text, uint64_t len, DevBuf<char>&
   STB_CUDA(ctx, d_len.alloc(1, ctx.stream));
   {
     Launch l(ctx, "fasta_lines");
-    fasta_tile_kernel<0><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, run_sums.ptr, nullptr, nullptr, nullptr, nullptr);
+    fasta_tile_kernel<0><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, run_sums.ptr, nullptr, nullptr, nullptr, nullptr, d_text);
   }
   {
     Launch l(ctx, "fasta_scan");
-    fasta_scan_run_kernel<<<1, FX_THREADS, 0, ctx.stream>>>(run_sums.ptr, tiles, run_carry.ptr);
+    fasta_scan_run_kernel<<<1, FX_THREADS, 0, ctx.stream>>>(run_sums.ptr, tiles, run_carry.ptr, nullptr);
   }
   {
     Launch l(ctx, "fasta_count");
-    fasta_tile_kernel<1><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, nullptr, run_carry.ptr, tile_sums.ptr, nullptr, nullptr);
+    fasta_tile_kernel<1><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, nullptr, run_carry.ptr, tile_sums.ptr, nullptr, nullptr, d_text);
   }
   {
     Launch l(ctx, "fasta_scan");
-    fasta_scan_skip_kernel<<<1, FX_THREADS, 0, ctx.stream>>>(tile_sums.ptr, run_carry.ptr, tiles, carry.ptr, d_len.ptr);
+    fasta_scan_skip_kernel<<<1, FX_THREADS, 0, ctx.stream>>>(tile_sums.ptr, run_carry.ptr, tiles, carry.ptr, d_len.ptr, nullptr);
   }
   {
     Launch l(ctx, "fasta_emit");
-    fasta_tile_kernel<2><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, nullptr, nullptr, nullptr, carry.ptr, body.ptr);
+    fasta_tile_kernel<2><<<tiles, FX_THREADS, 0, ctx.stream>>>(d_text, len, nullptr, nullptr, nullptr, carry.ptr, body.ptr, d_text);
   }
   unsigned long long h = 0;
   STB_CUDA(ctx, cudaMemcpyAsync(&h, d_len.ptr, 8, cudaMemcpyDeviceToHost, ctx.stream));
+  STB_CUDA(ctx, cudaStreamSynchronize(ctx.stream));
+  STB_CUDA(ctx, cudaGetLastError());
+  *body_len = h;
+  return STB_OK;
+}
+
+// ---- the same, chunk by chunk (streaming ingest from host memory) --------------------------------
+// The text arrives in chunks of a multiple of FX_TILE bytes in ONE contiguous device buffer; the
+// automaton's state at the end of a chunk (FxStream, on the device) is where the next chunk starts.
+struct FastaStreamImpl {
+  DevBuf<RunSum> run_sums, run_carry;
+  DevBuf<TileSum> tile_sums;
+  DevBuf<FxCarry> carry;
+  DevBuf<FxStream> state;
+  DevBuf<unsigned long long> d_len;
+};
+
+int fasta_stream_begin(Ctx& ctx, FastaStream& fs, uint64_t max_chunk_bytes) {
+  if (!fs.impl) fs.impl = std::make_shared<FastaStreamImpl>();
+  auto& im = *static_cast<FastaStreamImpl*>(fs.impl.get());
+  const uint64_t tiles = ceil_div(max_chunk_bytes, FX_TILE) + 1;
+  STB_CUDA(ctx, im.run_sums.ensure(tiles, ctx.stream));
+  STB_CUDA(ctx, im.run_carry.ensure(tiles, ctx.stream));
+  STB_CUDA(ctx, im.tile_sums.ensure(tiles, ctx.stream));
+  STB_CUDA(ctx, im.carry.ensure(tiles, ctx.stream));
+  STB_CUDA(ctx, im.state.ensure(1, ctx.stream));
+  STB_CUDA(ctx, im.d_len.ensure(1, ctx.stream));
+  const FxStream init{RunSum{1u, 0u}, 0u, 0u, 0ull};
+  STB_CUDA(ctx, cudaMemcpyAsync(im.state.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
+  STB_CUDA(ctx, cudaStreamSynchronize(ctx.stream));  // `init` is stack memory
+  return STB_OK;
+}
+
+int fasta_stream_chunk(Ctx& ctx, FastaStream& fs, const char* d_text_begin, uint64_t first, uint64_t len, char* d_body) {
+  auto& im = *static_cast<FastaStreamImpl*>(fs.impl.get());
+  if (len == 0) return STB_OK;
+  if (first % FX_TILE) return ctx.fail(STB_ERR_INVALID_ARG, "fasta stream: chunk start must be a multiple of the extraction tile");
+  const char* text = d_text_begin + first;
+  const uint32_t tiles = (uint32_t)ceil_div(len, FX_TILE);
+  cudaStream_t st = ctx.stream;
+  {
+    Launch l(ctx, "fasta_lines");
+    fasta_tile_kernel<0><<<tiles, FX_THREADS, 0, st>>>(text, len, im.run_sums.ptr, nullptr, nullptr, nullptr, nullptr, d_text_begin);
+  }
+  {
+    Launch l(ctx, "fasta_scan");
+    fasta_scan_run_kernel<<<1, FX_THREADS, 0, st>>>(im.run_sums.ptr, tiles, im.run_carry.ptr, im.state.ptr);
+  }
+  {
+    Launch l(ctx, "fasta_count");
+    fasta_tile_kernel<1><<<tiles, FX_THREADS, 0, st>>>(text, len, nullptr, im.run_carry.ptr, im.tile_sums.ptr, nullptr, nullptr, d_text_begin);
+  }
+  {
+    Launch l(ctx, "fasta_scan");
+    fasta_scan_skip_kernel<<<1, FX_THREADS, 0, st>>>(im.tile_sums.ptr, im.run_carry.ptr, tiles, im.carry.ptr, im.d_len.ptr, im.state.ptr);
+  }
+  {
+    Launch l(ctx, "fasta_emit");
+    fasta_tile_kernel<2><<<tiles, FX_THREADS, 0, st>>>(text, len, nullptr, nullptr, nullptr, im.carry.ptr, d_body, d_text_begin);
+  }
+  return STB_OK;
+}
+
+int fasta_stream_body_len(Ctx& ctx, FastaStream& fs, uint64_t* body_len) {
+  auto& im = *static_cast<FastaStreamImpl*>(fs.impl.get());
+  unsigned long long h = 0;
+  STB_CUDA(ctx, cudaMemcpyAsync(&h, im.d_len.ptr, 8, cudaMemcpyDeviceToHost, ctx.stream));
   STB_CUDA(ctx, cudaStreamSynchronize(ctx.stream));
   STB_CUDA(ctx, cudaGetLastError());
   *body_len = h;

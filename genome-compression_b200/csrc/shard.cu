@@ -326,14 +326,24 @@ apply_answers_kernel(PeerHome home, uint32_t world, uint32_t* __restrict__ aux, 
   const uint32_t count = min(*reinterpret_cast<const volatile uint32_t*>(home.base[owner] + home.ans_count_off + 4ull * home.self), home.ans_cap);
   const unsigned long long* list = reinterpret_cast<const unsigned long long*>(home.base[owner] + home.ans_off) + (uint64_t)home.self * home.ans_cap;
   const uint32_t mask = (1u << home.log2_positions) - 1u;
-  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < count; i += gridDim.x * 256) {
-    const unsigned long long a = __ldcs(list + i);
-    const uint32_t p = (uint32_t)(a >> 32) & mask, fp = (uint32_t)a;
-    if (fp == 0xffffffffu) {
-      atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
-    } else {
-      atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
-      atomicOr(aux + p, fp);
+  // four loads in flight per thread: the lists of the other ranks answer after a few microseconds
+  for (uint32_t i0 = (blockIdx.x * 256 + threadIdx.x); i0 < count; i0 += gridDim.x * 256 * 4) {
+    unsigned long long a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t i = i0 + k * gridDim.x * 256;
+      a[k] = i < count ? __ldcs(list + i) : ~0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a[k] == ~0ull) continue;
+      const uint32_t p = (uint32_t)(a[k] >> 32) & mask, fp = (uint32_t)a[k];
+      if (fp == 0xffffffffu) {
+        atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
+      } else {
+        atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
+        atomicOr(aux + p, fp);
+      }
     }
   }
   (void)world;
@@ -411,6 +421,7 @@ struct Shard : Ctx {
     const uint64_t per = std::max<uint64_t>(1, ceil_div(n, world));
     shard = 1;
     while (shard < per) shard <<= 1;
+    // below this many positions a level costs less on one GPU than its three barriers cost the world
     cut = opt_cut ? opt_cut : std::max<uint64_t>(1ull << 20, (1ull << 25) / world);
     pointer_levels = 1;
     while ((shard >> pointer_levels) >= 1 && level_total(pointer_levels) > cut && level_total(pointer_levels) > 1) ++pointer_levels;
@@ -572,7 +583,10 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     }
     STB_CUDA(s, cudaMemsetAsync(s.totals_all.ptr, 0, world * 4, st));
   }
-  STB_TRY(comm.all_reduce_min(s, s.dminpos.ptr, canon_entries));
+  {
+    Launch l(s, "collective_leaf_min", false);
+    STB_TRY(comm.all_reduce_min(s, s.dminpos.ptr, canon_entries));
+  }
   {
     const uint32_t tiles = (uint32_t)ceil_div(n0, LVL_TILE), chunks = tiles / CHUNK_TILES + 1;
     uint32_t* chunkcnt = s.tilecnt.ptr + tiles;
@@ -618,13 +632,19 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     STB_CUDA(s, cudaMemsetAsync(s.arena + s.off_ans_count, 0, STB_MAX_RANKS * 4, st));
     STB_TRY(shard_partition(s, sb, ptr_cur, (uint32_t)n_cur_local, (uint32_t)n_next_local, (uint32_t)lo, child_first, child_multi, aux, first_bits,
                             seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
-    STB_TRY(comm.barrier(s));  // every rank's buckets are complete: the owners pull them
+    {
+      Launch l(s, "collective_barrier", false);
+      STB_TRY(comm.barrier(s));  // every rank's buckets are complete: the owners pull them
+    }
     STB_CUDA(s, s.count2.ensure((uint64_t)local1 << sb.b2, st));
     STB_TRY(shard_dedup(s, sb, s.ws, s.count2.ptr, s.scalars.ptr + 3));
-    STB_TRY(comm.barrier(s));  // every owner's answer lists are complete: the home ranks pull them
+    {
+      Launch l(s, "collective_barrier", false);
+      STB_TRY(comm.barrier(s));  // every owner's answer lists are complete: the home ranks pull them
+    }
     {
       Launch l(s, "shard_apply");
-      apply_answers_kernel<<<dim3(148, world), 256, 0, st>>>(sb.home, (uint32_t)world, aux, first_bits, multi_bits);
+      apply_answers_kernel<<<dim3(1184, world), 256, 0, st>>>(sb.home, (uint32_t)world, aux, first_bits, multi_bits);
     }
     // ids: local counts -> the world's totals -> this rank's base
     const uint32_t tiles = (uint32_t)ceil_div(n_next_local, LVL_TILE), chunks = tiles / CHUNK_TILES + 1;
@@ -636,7 +656,10 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     }
     sum_chunks_kernel<<<1, 256, 0, st>>>(chunkcnt, chunks, s.scalars.ptr);
     uint32_t* totals = s.totals_all.ptr + (uint64_t)(j + 1) * world;
-    STB_TRY(comm.all_gather_u32(s, s.scalars.ptr, totals, 1));
+    {
+      Launch l(s, "collective_totals", false);
+      STB_TRY(comm.all_gather_u32(s, s.scalars.ptr, totals, 1));
+    }
     id_base_kernel<<<1, 1, 0, st>>>(totals, rank, world, s.scalars.ptr + 1, s.scalars.ptr + 2);
     s.slices.emplace_back();
     STB_CUDA(s, s.slices.back().alloc(std::max<uint64_t>(n_next_local, 1), st));
@@ -646,7 +669,10 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
       assign_kernel<MODE_NODE><<<tiles, LVL_THREADS, 0, st>>>(ptr_nxt, (uint32_t)n_next_local, none, first_bits, s.tilecnt.ptr, chunkcnt, 0u, nullptr,
                                                               s.scalars.ptr + 5, s.slices.back().ptr, S, ptr_cur, (uint32_t)n_cur_local, s.scalars.ptr + 1);
     }
-    STB_TRY(comm.barrier(s));
+    {
+      Launch l(s, "collective_barrier", false);
+      STB_TRY(comm.barrier(s));  // every rank's first occurrences have their ids
+    }
     if (tiles) {
       Launch l(s, "shard_resolve");
       shard_resolve_kernel<<<tiles, LVL_THREADS, 0, st>>>(aux, ptr_nxt, (uint32_t)n_next_local, first_bits, sb.home, s.off_ptr[cur_which ^ 1]);
@@ -660,6 +686,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   STB_TRY(comm.barrier(s));  // every rank's last pointer array is final
   const uint64_t n_top = s.level_total(L - 1);
   if (rank == 0) {
+    Launch l(s, "root_top_levels", false);
     DevBuf<uint32_t> top;
     STB_CUDA(s, top.alloc(n_top, st));
     for (int r = 0; r < world; ++r) {

@@ -85,6 +85,15 @@ struct Tree : Ctx {
 // FASTA text (device) -> bare body (device, newly allocated).  body_len excludes
 // nothing yet (tail truncation happens at packing).
 int fasta_extract_body(Ctx& ctx, const char* d_text, uint64_t len, DevBuf<char>& body, uint64_t* body_len);
+// The same chunk by chunk: the text lies in one contiguous device buffer and arrives in chunks (multiples
+// of 64 KiB); the automaton's state is carried on the device; the body grows in d_body.
+struct FastaStream {
+  std::shared_ptr<void> impl;
+};
+constexpr uint64_t FASTA_STREAM_ALIGN = 65536;
+int fasta_stream_begin(Ctx& ctx, FastaStream& fs, uint64_t max_chunk_bytes);
+int fasta_stream_chunk(Ctx& ctx, FastaStream& fs, const char* d_text_begin, uint64_t first, uint64_t len, char* d_body);
+int fasta_stream_body_len(Ctx& ctx, FastaStream& fs, uint64_t* body_len);  // synchronises: body bytes produced so far
 // bare body (device) -> packed leaves (device); error on unknown symbols.
 int pack_body(Ctx& ctx, const char* d_body, uint64_t n_leaves, unsigned long long* d_leaves);
 
@@ -92,6 +101,7 @@ int pack_body(Ctx& ctx, const char* d_body, uint64_t n_leaves, unsigned long lon
 int build_from_body(Tree& t, const char* d_body, uint64_t body_len);
 int build_from_leaves(Tree& t, const unsigned long long* d_leaves, uint64_t n);
 int build_from_host_body(Tree& t, const char* h_body, uint64_t body_len);  // streaming; -1 = use the one-shot path
+int build_from_host_fasta(Tree& t, const char* h_text, uint64_t len);      // streaming incl. body extraction; -1 = use the one-shot path
 int build_upper_levels(Tree& t, const uint32_t* d_ptrs, uint64_t n, bool at_least_one);
 int dist_leaf_direct_minpos(Ctx& ctx, const char* d_body, uint64_t n_local, uint64_t gpos0, uint32_t* dminpos, uint32_t* tmp,
                             int* non_acgt);

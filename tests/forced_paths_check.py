@@ -43,6 +43,19 @@ def main():
             assert host.layer_counts() == want2.layer_counts(), (name, S, "host body")
             assert host.serialize() == want2.serialize(), (name, S, "host body")
             assert np.array_equal(host.decode(), leaves)
+    # FASTA text in HOST memory: headers, wrapped lines, blank lines, several records (streams chunk by chunk
+    # with the line automaton's state carried across the chunks when the stream options say so)
+    def wrap(b, w):
+        return b"\n".join(b[i:i + w] for i in range(0, len(b), w))
+    for S in (12, 5):
+        fasta = (b">rec one\n" + wrap(corpus_text("merged"), 60) + b"\n>rec two | x\n" + wrap(corpus_text("vaccg").upper(), 71) +
+                 b"\n>three\n" + wrap(corpus_text("hehcmv"), 4097) + b"\n>four\n" + corpus_text("humhbb") + b"\n")
+        lv = oracle.fasta_to_leaves(fasta, S)
+        got = stb.SharedTree(S).build_from_fasta(fasta)
+        want = oracle.build(lv, S)
+        assert got.layer_counts() == want.layer_counts(), ("fasta host", S)
+        assert got.serialize() == want.serialize(), ("fasta host", S)
+        assert np.array_equal(got.decode(), lv)
     n = 7_000_000
     buf = torch.empty(n, dtype=torch.uint8, device="cuda")
     stb.synth_genome(buf, n, seed=11, repeat_permille=500)
