@@ -509,7 +509,41 @@ def run_b200(args):
                 "value": bases_used / dwarm_s / 1e9, "unit": "Gbp/s", "ms": round(dwarm_s * 1e3, 2), "first_call_ms": round(dcold_s * 1e3, 2),
                 "h2d_bytes": int(stream_bytes), "d2h_bytes": n0 * DNA, "roundtrip_equal": e2e_roundtrip,
                 "path": "stb_deserialize(host bytes) + stb_decode_ascii(HOST)"}
-            del host, dag_host, text_host, back
+            # ---- BASELINE.json config 3 as a FASTA file: a '>' header line and 60-column lines, from pinned host memory.
+            # Same body, so the same tree: the stream must equal the reference's again.  (stb_build_from_fasta(STB_HOST):
+            # chunked copy, body extraction with the line automaton's state carried across chunks, build behind the copy.)
+            import numpy as np
+            body_np = host[: (n_bases // 60) * 60].numpy().reshape(-1, 60)
+            header = np.frombuffer(b">synthetic genome, config 3\n", dtype=np.uint8)
+            rest = host[(n_bases // 60) * 60:].numpy()
+            fasta_len = header.size + body_np.shape[0] * 61 + rest.size + 1
+            fasta_host = torch.empty(fasta_len, dtype=torch.uint8, pin_memory=True)
+            fview = fasta_host.numpy()
+            fview[: header.size] = header
+            lines = fview[header.size: header.size + body_np.shape[0] * 61].reshape(-1, 61)
+            lines[:, :60] = body_np
+            lines[:, 60] = 10
+            fview[header.size + body_np.shape[0] * 61: fasta_len - 1] = rest
+            fview[fasta_len - 1] = 10
+            del body_np, lines, fview
+            tree.build_from_fasta(fasta_host)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps_f = max(1, min(args.steps, 3))
+            for _ in range(reps_f):
+                tree.build_from_fasta(fasta_host)
+                _ = (tree.width(), tree.node_count())
+            torch.cuda.synchronize()
+            fasta_s = (time.perf_counter() - t0) / reps_f
+            fasta_counts = tree.layer_counts()
+            tree.sort()
+            tree.serialize_to_host(dag_host)
+            parity["e2e_fasta_sha256"] = __import__("hashlib").sha256(dag_host[:stream_bytes].numpy().tobytes()).hexdigest()
+            pipeline["e2e_fasta"] = {
+                "value": bases_used / fasta_s / 1e9, "unit": "Gbp/s", "ms": round(fasta_s * 1e3, 2), "h2d_bytes": int(fasta_len),
+                "layout": "one '>' header line, 60-column lines", "vs_bare_body_e2e": round(fasta_s * 1e3 / e2e["ms_per_step"], 3) if e2e else None,
+                "layer_counts_equal": fasta_counts == U[1:], "path": "stb_build_from_fasta(STB_HOST)"}
+            del host, dag_host, text_host, back, fasta_host
         del dag
         if gold:
             check_against_golden(gold, "per-layer node counts", parity["layer_counts"], gold["layer_counts"])
@@ -518,6 +552,8 @@ def run_b200(args):
             check_against_golden(gold, "stream sha256 after sort_tree", parity["post_sort_sha256"], gold["post_sha256"])
             check_against_golden(gold, "stream length", int(stream_bytes), gold["post_bytes"])
             check_against_golden(gold, "sha256 of the 10 M operator[] answers", parity["query_answers_sha256"], gold["query_answers_sha256"])
+            if "e2e_fasta_sha256" in parity:
+                check_against_golden(gold, "stream sha256 of the FASTA-file build (header + 60-column lines)", parity["e2e_fasta_sha256"], gold["post_sha256"])
             if "e2e_compress_sha256" in parity:
                 check_against_golden(gold, "stream sha256 of the end-to-end compress path", parity["e2e_compress_sha256"], gold["post_sha256"])
             parity["equal_to_reference"] = True
@@ -622,6 +658,11 @@ def run_b200_dist(args, world, rank, local_rank):
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     prof = me.profile_read()
     me.profile(False)
+    if os.environ.get("STB_RANK_PROFILES"):  # per-rank kernel classes, for finding the rank the others wait for
+        out_dir = ROOT / "gpurun_out"
+        out_dir.mkdir(exist_ok=True)
+        (out_dir / f"rank_profile_n{world}_r{rank}.json").write_text(json.dumps(
+            {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}))
     ms_per_step = float(ms.item()) / args.steps
     bases_used = n_leaves * DNA
     value = bases_used / (ms_per_step * 1e-3) / 1e9

@@ -89,6 +89,7 @@ def _load() -> C.CDLL:
         "stb_profile_reset": [vp],
         "stb_profile_read": [vp, P(cp), P(C.c_double), P(u64), u64, P(u64)],
         "stb_synth_genome": [i32, vp, vp, u64, u64, u64, u64, u32],
+        "stb_synth_mask": [i32, vp, vp, u64, u64, u64],
         # include/shared_tree_b200_dist.h
         "stb_dist_pack_body": [vp, vp, u64, vp],
         "stb_dist_partition": [vp, i32, vp, u64, u64, i32, vp, vp, vp, vp],
@@ -362,6 +363,15 @@ def synth_genome(out_device_tensor, n_bases: int, first: int = 0, count: int | N
     if st != 0:
         raise StbError(st, lib.stb_status_string(st).decode())
     return out_device_tensor
+
+
+def synth_mask(text_device_tensor, first: int = 0, count: int | None = None, seed: int = 42, device: int = 0, stream: int | None = None):
+    """Lays N runs (about 1 % of the bases) and soft-masked lower-case stretches over a generated text, in place."""
+    count = text_device_tensor.numel() if count is None else count
+    st = lib.stb_synth_mask(device, C.c_void_p(stream or 0), text_device_tensor.data_ptr(), first, count, seed)
+    if st != 0:
+        raise StbError(st, lib.stb_status_string(st).decode())
+    return text_device_tensor
 
 
 def node_canonical(left: int, right: int):

@@ -30,6 +30,7 @@ namespace {
 
 constexpr int PT_ITEMS = 4;                     // records per thread; a CTA tile is PT_ITEMS * its thread count
 constexpr int PT_MAX_BUCKETS = 512;             // at most 9 bits per pass
+static_assert(1024 * PT_ITEMS <= COLLAPSE_WINDOW, "a run's head is at most one partition tile before its positions");
 constexpr size_t pt_smem(int threads) { return (size_t)threads * PT_ITEMS * (8 + 4 + 2) + 3 * PT_MAX_BUCKETS * 4; }
 
 constexpr int DD_CAP = 3072;                    // records of a final bucket, held in registers (DD_CAP / threads each)
@@ -59,8 +60,8 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
                  const uint32_t* __restrict__ in_count, uint32_t in_cap,
                  unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
                  uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
-                 const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi, uint32_t* __restrict__ overflow,
-                 uint32_t segs, uint32_t pos_base, PeerDest peer) {
+                 uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
+                 uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, PeerDest peer) {
   constexpr int PT_TILE = PT_THREADS * PT_ITEMS, PT_WARPS = PT_THREADS / 32;
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
@@ -96,6 +97,9 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
 
   unsigned long long key[PT_ITEMS];
   uint32_t pos[PT_ITEMS], dr[PT_ITEMS];
+  uint32_t flag_of[PT_ITEMS];
+  bool collapsed[PT_ITEMS];
+  __shared__ uint32_t shead[PT_TILE / 32];  // FROM_CHILDREN: bit per tile position, set for the positions that are not collapsed
   if (!FROM_CHILDREN) {
     // all of a thread's loads are issued before the first one is used: a segment pulled over NVLink
     // answers after a few microseconds, and only bytes in flight hide that
@@ -115,15 +119,9 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     dr[it] = 0xffffffffu;
     if (FROM_CHILDREN) {
       pos[it] = pos_base + i;
-      // every position starts as a first occurrence; the dedup kernel clears the later ones
-      const uint32_t word = __ballot_sync(0xffffffffu, valid);
-      if (lane == 0 && word) first_bits[i >> 5] = word;
-      if (valid && child_first) {  // a child that never repeats: the only node with that child, no record
-        const uint32_t repeats = ~__ldg(child_first + (i >> 4)) | __ldg(child_multi + (i >> 4));
-        valid = ((repeats >> ((2u * i) & 31u)) & 3u) == 3u;
-      }
+      uint32_t l = 0, r = 0;
+      bool same = false;  // the same children as the position before it (runs of N, of one letter, of a short period)
       if (valid) {
-        uint32_t l, r, cl, cr, f;
         if (2 * (uint64_t)i + 1 < n_cur) {
           const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + i);
           l = pr.x;
@@ -132,10 +130,35 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
           l = cur[2 * (uint64_t)i];
           r = PTR_NULL;
         }
+        if (it * PT_THREADS + tid > 0) {  // never the first position of a tile: every tile keeps a head
+          const uint2 before = __ldg(reinterpret_cast<const uint2*>(cur) + i - 1);
+          same = before.x == l && before.y == r;
+        }
+      }
+      // Runs collapse here: a position that repeats its predecessor makes no record (a genome's N runs
+      // would otherwise put millions of equal keys into one bucket); it is a later occurrence of the
+      // run's head, which stands for the run.  Every other position starts as a first occurrence; the
+      // dedup kernel clears the later ones.
+      const uint32_t heads = __ballot_sync(0xffffffffu, valid && !same);
+      const uint32_t word_at = (it * PT_THREADS + tid) >> 5;
+      if (lane == 0) {
+        shead[word_at] = heads;
+        if (heads) first_bits[i >> 5] = heads;
+      }
+      collapsed[it] = valid && same;
+      if (valid && !same && child_first) {  // a child that never repeats: the only node with that child, no record
+        const uint32_t repeats = ~__ldg(child_first + (i >> 4)) | __ldg(child_multi + (i >> 4));
+        valid = ((repeats >> ((2u * i) & 31u)) & 3u) == 3u;
+      } else if (same) {
+        valid = false;
+      }
+      uint32_t cl, cr, f = 0;
+      if (valid || collapsed[it]) {
         canonical_node(l, r, cl, cr, f);
         key[it] = pair_key(cl, cr);
-        aux[i] = f;  // flags at bits 29..31; the dedup kernel ORs the first occurrence's position below them
+        if (valid) aux[i] = f;  // flags at bits 29..31; the dedup kernel ORs the first occurrence's position below them
       }
+      flag_of[it] = f;
     }
     if (valid) {
       const uint32_t d = (uint32_t)(bucket_hash(key[it]) >> shift) & (nb - 1u);
@@ -143,6 +166,21 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     }
   }
   __syncthreads();
+  if (FROM_CHILDREN) {
+#pragma unroll
+    for (int it = 0; it < PT_ITEMS; ++it) {
+      const uint32_t o = it * PT_THREADS + tid;  // offset in the tile
+      if (collapsed[it]) {
+        // the run's head: the nearest position at or before this one that is not collapsed
+        uint32_t w = o >> 5;
+        uint32_t m = shead[w] & (0xffffffffu >> (31u - (o & 31u)));
+        while (m == 0u) m = shead[--w];
+        const uint32_t head = (w << 5) + 31u - (uint32_t)__clz(m);
+        aux[first + o] = flag_of[it] | (pos_base + first + head);
+        if (head + 1u == o && multi_bits) atomicOr(multi_bits + ((first + head) >> 5), 1u << ((first + head) & 31u));  // the head occurs again
+      }
+    }
+  }
   // exclusive scan of the tile's bucket counts; one global reservation per bucket
   {
     const uint32_t c = tid < nb ? hist[tid] : 0u;
@@ -329,8 +367,8 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt) {
 
 template <int T>
 static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
-                             const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* count1,
-                             uint32_t* count2, uint32_t* overflow) {
+                             const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
+                             uint32_t* count1, uint32_t* count2, uint32_t* overflow) {
   cudaStream_t st = ctx.stream;
   constexpr int TILE = T * PT_ITEMS;
   const size_t smem = pt_smem(T);
@@ -339,15 +377,15 @@ static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl
   {
     Launch l(ctx, "bucket_partition");
     partition_kernel<true, T, false><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(
-        cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits, child_first,
-        child_multi, overflow, 1u, 0u, PeerDest{});
+        cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits, multi_bits,
+        child_first, child_multi, overflow, 1u, 0u, PeerDest{});
   }
   {
     Launch l(ctx, "bucket_partition");
     const dim3 grid((unsigned)ceil_div(pl.cap1, TILE), 1u << pl.b1);
     partition_kernel<false, T, false><<<grid, T, smem, st>>>(nullptr, 0u, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr, ws.pos2.ptr,
-                                                             count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, overflow, 1u,
-                                                             0u, PeerDest{});
+                                                             count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, nullptr, overflow,
+                                                             1u, 0u, PeerDest{});
   }
   return STB_OK;
 }
@@ -367,15 +405,15 @@ constexpr int SH_PT = 512, SH_DD = 512;
 
 // Step 1 of a sharded level: this rank's positions -> records in its own first-pass buckets (the owners pull them).
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
-                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, unsigned long long* seg_keys,
-                    uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow) {
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
+                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow) {
   const size_t smem = pt_smem(SH_PT);
   STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, SH_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (n_next == 0) return STB_OK;
   Launch l(ctx, "shard_partition");
   partition_kernel<true, SH_PT, false><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
-      cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, child_first,
-      child_multi, overflow, 1u, pos_base, PeerDest{});
+      cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, multi_bits,
+      child_first, child_multi, overflow, 1u, pos_base, PeerDest{});
   return STB_OK;
 }
 
@@ -394,7 +432,7 @@ int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, uint32_t*
     Launch l(ctx, "shard_partition2");
     const dim3 grid((unsigned)ceil_div(sb.cap_seg, SH_PT * PT_ITEMS), local1 * sb.dest.world);
     partition_kernel<false, SH_PT, true><<<grid, SH_PT, smem, st>>>(nullptr, 0u, 0u, nullptr, nullptr, nullptr, sb.cap_seg, ws.keys2.ptr, ws.pos2.ptr, count2,
-                                                                    sb.cap2, 64 - sb.b1 - sb.b2, sb.b2, nullptr, nullptr, nullptr, nullptr, overflow,
+                                                                    sb.cap2, 64 - sb.b1 - sb.b2, sb.b2, nullptr, nullptr, nullptr, nullptr, nullptr, overflow,
                                                                     sb.dest.world, 0u, sb.dest);
   }
   {
@@ -426,9 +464,9 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, cons
   uint32_t* overflow = count2 + nb;
   STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 1) * 4, st));
   if (pl.partition_threads == 512)
-    STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, count1, count2, overflow));
+    STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow));
   else
-    STB_TRY(launch_partitions<1024>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, count1, count2, overflow));
+    STB_TRY(launch_partitions<1024>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow));
   if (pl.dedup_threads == 256) STB_TRY(launch_dedup<256>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else if (pl.dedup_threads == 512) STB_TRY(launch_dedup<512>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else STB_TRY(launch_dedup<1024>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));

@@ -19,6 +19,10 @@ struct BucketPlan {
 // ---- sharded build: records and answers travel through peer-mapped memory --------------------
 constexpr int STB_MAX_RANKS = 16;
 
+// A position that repeats its predecessor makes no record: it points at the head of its run, at most one
+// partition tile before it.  Only a first occurrence that close needs the resolve kernels' second look.
+constexpr uint32_t COLLAPSE_WINDOW = 4096;
+
 struct PeerDest {               // the first-pass buckets of every rank (a source keeps what it makes; owners pull)
   char* base[STB_MAX_RANKS] = {};  // the arena of every rank (own included)
   uint64_t keys_off = 0, pos_off = 0, count_off = 0;  // bucket arrays and their record counts inside an arena
@@ -63,8 +67,8 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan, co
 // shard.cu drives these: see ShardBuckets.  seg_*: this rank's first-pass buckets (2^b1 x cap_seg records and
 // their counts, in its arena); the owner's split reads every rank's through `dest`.
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
-                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, unsigned long long* seg_keys,
-                    uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow);
+                    const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
+                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow);
 int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, uint32_t* count2, uint32_t* overflow);
 
 }  // namespace stb

@@ -35,9 +35,50 @@ namespace stb {
 
 struct BuildFlags {
   unsigned long long bad_symbol;  // (byte offset << 8) | upper-cased byte; ~0 = none
-  uint32_t non_acgt;              // direct leaf mode met a non-ACGT leaf
+  uint32_t non_acgt;              // direct leaf mode cannot hold this input's leaves (no side table, or it filled up)
   uint32_t bad_leaf;              // packed input leaf with bits >= 4S
+  uint32_t side_claims;           // distinct leaves in the side table
+  uint32_t pad;
 };
+
+// Leaves with symbols outside ACGT (N runs, IUPAC codes) next to a direct-addressed ACGT table: they
+// go to a small hash table (the level's `slots` / `cap` in direct mode) keyed by the canonical
+// 4-bit word.  Real genomes have few distinct ones (all-N, and what borders on an N run), so the
+// table is small; an input with more distinct such leaves than it holds raises non_acgt and the
+// host rebuilds with the hash-table leaf level.  Returns the slot, or ~0 when it gave up.
+__device__ __forceinline__ uint32_t side_insert(const LevelTable& tab, unsigned long long key, uint32_t pos, BuildFlags* flags) {
+  if (tab.cap == 0u || *reinterpret_cast<volatile uint32_t*>(&flags->side_claims) > tab.cap / 2u) {
+    flags->non_acgt = 1u;
+    return 0xffffffffu;
+  }
+  uint32_t s = __umulhi(hash64(key), tab.cap);
+  for (uint32_t steps = 0; steps < 8192u; ++steps) {
+    unsigned long long k;
+    uint32_t mp;
+    load_slot(tab.slots + s, k, mp);
+    if (k == EMPTY_KEY) {
+      claim_slot(tab.slots + s, key, pos, k, mp);
+      if (k == EMPTY_KEY) {  // claimed: key and min-position written together
+        atomicAdd(&flags->side_claims, 1u);
+        if (tab.first_bits) toggle_bit(tab.first_bits, pos);
+        return s;
+      }
+    }
+    if (k == key) {
+      if (mp > pos) {
+        const uint32_t old = atomicMin(&tab.slots[s].minpos, pos);
+        if (tab.first_bits && old > pos) {
+          toggle_bit(tab.first_bits, pos);
+          toggle_bit(tab.first_bits, old);
+        }
+      }
+      return s;
+    }
+    if (++s == tab.cap) s = 0;
+  }
+  flags->non_acgt = 1u;
+  return 0xffffffffu;
+}
 
 template <bool DIRECT>
 __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_t pos, const LevelTable& tab,
@@ -47,8 +88,8 @@ __device__ __forceinline__ void insert_leaf(unsigned long long v, int S, uint32_
   uint32_t s;
   if (DIRECT) {
     if (!leaf_is_acgt(v, S)) {
-      flags->non_acgt = 1u;
-      *tmp_at_pos = 0u;
+      const uint32_t side = side_insert(tab, canon, pos, flags);
+      *tmp_at_pos = side == 0xffffffffu ? 0u : (LEAF_SIDE | side | f);
       return;
     }
     s = leaf_to_2bit(canon);
@@ -132,9 +173,17 @@ leaf_insert_acgt12_kernel(const char* __restrict__ body, uint64_t n_leaves, Leve
     if (j >= here) continue;
     uint32_t c0, c1, c2;
     const bool ok = acgt_word_to_2bit(words[3 * j], c0) & acgt_word_to_2bit(words[3 * j + 1], c1) & acgt_word_to_2bit(words[3 * j + 2], c2);
-    if (!ok) {
-      flags->non_acgt = 1u;
-      tmp[tile_first + j] = 0u;
+    if (!ok) {  // a symbol outside ACGT: the general 4-bit pack of this one leaf, into the side table
+      uint32_t bad = 0xFFFFFFFFu, f4;
+      const unsigned long long v = pack_leaf<12>(smem, tile, j, 12, bad);
+      if (bad != 0xFFFFFFFFu) {
+        uint32_t ch = tile[bad];
+        if (ch >= 'a' && ch <= 'z') ch -= 32;
+        atomicMin(&flags->bad_symbol, ((tile_first * 12 + bad) << 8) | ch);
+      }
+      const unsigned long long canon = canonical_leaf(v, 12, f4);
+      const uint32_t side = side_insert(tab, canon, pos0 + (uint32_t)(tile_first + j), flags);
+      tmp[tile_first + j] = side == 0xffffffffu ? 0u : (LEAF_SIDE | side | f4);
       continue;
     }
     const uint32_t c = c0 | (c1 << 8) | (c2 << 16);
@@ -257,13 +306,18 @@ resolve_kernel(const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, c
         const uint32_t t = aux[p];
         const uint32_t s = t & IDX_MASK;
         uint32_t id;
-        if (MODE == RESOLVE_DIRECT) {
+        if (MODE == RESOLVE_DIRECT && !(s & LEAF_SIDE)) {
           id = __ldcg(tab.dids + s);
+        } else if (MODE == RESOLVE_DIRECT) {  // a side-table leaf: its first occurrence's finished pointer has the id
+          id = __ldcg(out + __ldcg(&tab.slots[s & (LEAF_SIDE - 1u)].minpos)) & IDX_MASK;
         } else {
           uint32_t q = s;
           if (!firstpos) {
             q = __ldcg(&tab.slots[s].minpos);
             if (multi_bits) atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
+          } else if (p - q < COLLAPSE_WINDOW && !((__ldcg(bitmask + (q >> 5)) >> (q & 31u)) & 1u)) {
+            // p repeats its predecessor and q is the head of its run (bucket.cu), itself a later occurrence
+            q = __ldcg(aux + q) & IDX_MASK;
           }
           id = __ldcg(out + q) & IDX_MASK;
         }
@@ -472,7 +526,7 @@ struct Scratch {
   DevBuf<uint32_t> ptr_a, ptr_b, aux, bitmask, counts, dminpos, dids;
   DevBuf<uint32_t> lvl_bits[2], lvl_multi[2];  // node levels: first occurrences / first occurrences that occur again, by level parity
   DevBuf<uint32_t> tilecnt;                    // first occurrences per tile, then per chunk of tiles (count_kernel)
-  DevBuf<Slot> slots;
+  DevBuf<Slot> slots, side_slots;
   DevBuf<BuildFlags> flags;
   DevBuf<uint32_t> root;
   BucketWorkspace bucket;
@@ -513,6 +567,11 @@ Scratch& workspace_of(Tree& t) {
     sc.stream_tags_cleared = false;
   }
   return sc;
+}
+
+// slots of the side table for leaves outside ACGT next to the direct table (side_insert)
+uint32_t side_table_cap(const Tree& t, uint64_t n0) {
+  return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n0), std::max<uint64_t>(1024, t.opt.side_table_slots));
 }
 
 uint32_t table_cap(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, 2 * n), 0x1ffffffeull); }
@@ -766,7 +825,7 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   STB_CUDA(t, sc.bitmask.ensure(bitmap_words(n0), st));
   STB_CUDA(t, sc.flags.ensure(1, st));
   {
-    BuildFlags init{~0ull, 0u, 0u};
+    BuildFlags init{~0ull, 0u, 0u, 0u, 0u};
     STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
   }
 
@@ -786,15 +845,19 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   if (direct) {
     STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
     STB_CUDA(t, sc.dids.ensure(direct_entries, st));
+    STB_CUDA(t, sc.side_slots.ensure(side_table_cap(t, n0) + 1, st));
     tab.dminpos = sc.dminpos.ptr;
     tab.dids = sc.dids.ptr;
+    tab.slots = sc.side_slots.ptr;  // leaves with symbols outside ACGT (side_insert)
+    tab.cap = side_table_cap(t, n0);
     Launch l(t, "table_clear", false);
     STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
+    STB_CUDA(t, cudaMemsetAsync(sc.side_slots.ptr, 0xff, ((uint64_t)tab.cap + 1) * sizeof(Slot), st));
   } else {
     Launch l(t, "table_clear", false);
     STB_CUDA(t, cudaMemsetAsync(sc.slots.ptr, 0xff, ((uint64_t)leaf_cap + 1) * sizeof(Slot), st));
   }
-  const uint64_t leaf_store = direct ? std::min<uint64_t>(n0, direct_entries) : n0;
+  const uint64_t leaf_store = direct ? std::min<uint64_t>(n0, direct_entries / 2 + side_table_cap(t, n0) / 2 + 2) : n0;
   STB_CUDA(t, t.leaves.alloc(leaf_store, st));
 
   if (in.body) {
@@ -871,6 +934,8 @@ int stream_begin(Tree& t, Scratch& sc, StreamPlan& sp, uint64_t bound) {
   STB_CUDA(t, sc.flags.ensure(1, st));
   STB_CUDA(t, sc.dminpos.ensure(direct_entries, st));
   STB_CUDA(t, sc.dids.ensure(direct_entries, st));
+  STB_CUDA(t, sc.side_slots.ensure(side_table_cap(t, bound) + 1, st));
+  STB_CUDA(t, cudaMemsetAsync(sc.side_slots.ptr, 0xff, ((uint64_t)side_table_cap(t, bound) + 1) * sizeof(Slot), st));
   STB_TRY(reserve_node_workspace(t, sc, n[Lc]));  // the top of the tree, as in the one-shot build
   {
     bool grew = false;
@@ -887,14 +952,14 @@ int stream_begin(Tree& t, Scratch& sc, StreamPlan& sp, uint64_t bound) {
   STB_CUDA(t, cudaMemsetAsync(sc.counts.ptr, 0, 80 * 4, st));
   STB_CUDA(t, cudaMemsetAsync(sc.dminpos.ptr, 0xff, direct_entries * 4, st));
   {
-    BuildFlags init{~0ull, 0u, 0u};
+    BuildFlags init{~0ull, 0u, 0u, 0u, 0u};
     STB_CUDA(t, cudaMemcpyAsync(sc.flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     std::vector<uint32_t> sizes(Lc + 2, 0);
     for (int j = 0; j <= Lc; ++j) sizes[j] = (uint32_t)n[j];
     STB_CUDA(t, cudaMemcpyAsync(sc.level_sizes.ptr, sizes.data(), sizes.size() * 4, cudaMemcpyHostToDevice, st));
     STB_CUDA(t, cudaStreamSynchronize(st));  // `sizes` and `init` are stack memory
   }
-  STB_CUDA(t, t.leaves.alloc(std::min<uint64_t>(bound, direct_entries), st));
+  STB_CUDA(t, t.leaves.alloc(std::min<uint64_t>(bound, direct_entries / 2 + side_table_cap(t, bound) / 2 + 2), st));
   t.layers.clear();
   for (int j = 1; j <= Lc; ++j) {
     t.layers.emplace_back();
@@ -913,7 +978,7 @@ int stream_chunk(Tree& t, Scratch& sc, const StreamPlan& sp, const char* body, u
   cudaStream_t st = t.stream;
   uint32_t* const ptrs = sc.ptr_arena.ptr;
   uint32_t* const bits = sc.bit_arena.ptr;
-  LevelTable leaf_tab{nullptr, sc.dminpos.ptr, sc.dids.ptr, 0u};
+  LevelTable leaf_tab{sc.side_slots.ptr, sc.dminpos.ptr, sc.dids.ptr, side_table_cap(t, sp.bound)};
   leaf_tab.first_bits = bits;
   const uint64_t first = c * sp.C;
   if (S == 12) launch_leaf_text<12, true>(t, body + first * S, cnt, leaf_tab, ptrs + first, sc.flags.ptr, (uint32_t)first);
@@ -1130,7 +1195,7 @@ int dist_leaf_direct_minpos(Ctx& ctx, const char* d_body, uint64_t n_local, uint
   if (n_local == 0) return STB_OK;
   DevBuf<BuildFlags> flags;
   STB_CUDA(ctx, flags.alloc(1, ctx.stream));
-  BuildFlags init{~0ull, 0u, 0u};
+  BuildFlags init{~0ull, 0u, 0u, 0u, 0u};
   STB_CUDA(ctx, cudaMemcpyAsync(flags.ptr, &init, sizeof(init), cudaMemcpyHostToDevice, ctx.stream));
   LevelTable tab{nullptr, dminpos, nullptr, 0u};
   if (ctx.S == 12) launch_leaf_text<12, true>(ctx, d_body, n_local, tab, tmp, flags.ptr, (uint32_t)gpos0);

@@ -144,7 +144,7 @@ int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream) {
 static uint64_t* option_slot(Options& o, const char* name) {
   const struct { const char* name; uint64_t* slot; } table[] = {
       {"bucket_min", &o.bucket_min}, {"bucket_levels", &o.bucket_levels}, {"bucket_cap", &o.bucket_cap}, {"partition_threads", &o.partition_threads}, {"dedup_threads", &o.dedup_threads}, {"bucket_slack_permille", &o.bucket_slack_permille},
-      {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max}, {"reserve_pipeline", &o.reserve_pipeline},
+      {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max}, {"reserve_pipeline", &o.reserve_pipeline}, {"side_table_slots", &o.side_table_slots},
       {"stream_chunk_log2", &o.stream_chunk_log2}, {"stream_min_chunks", &o.stream_min_chunks}};
   for (const auto& e : table)
     if (std::strcmp(e.name, name) == 0) return e.slot;
@@ -538,6 +538,17 @@ int stb_synth_genome(int device, void* cuda_stream, char* out_device, uint64_t n
   ctx.device = device;
   ctx.stream = (cudaStream_t)cuda_stream;
   return synth_genome(ctx, out_device, n_bases, first, count, seed, repeat_permille);
+}
+
+int stb_synth_mask(int device, void* cuda_stream, char* text_device, uint64_t first, uint64_t count, uint64_t seed) {
+  if (!text_device && count) return STB_ERR_INVALID_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return STB_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return STB_ERR_CUDA;
+  Ctx ctx;
+  ctx.device = device;
+  ctx.stream = (cudaStream_t)cuda_stream;
+  return synth_mask(ctx, text_device, first, count, seed);
 }
 
 }  // extern "C"

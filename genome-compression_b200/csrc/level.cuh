@@ -31,6 +31,10 @@ __device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, 
 
 enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
 
+// direct leaf mode: a per-position word with this bit names a slot of the side table (a leaf with
+// symbols outside ACGT) instead of a 2-bit code of the direct table (codes are below 2^24)
+constexpr uint32_t LEAF_SIDE = 1u << 28;
+
 // Loads the tile's 32 bitmap words (one per warp and iteration), leaves the exclusive prefix of
 // their popcounts in word_pref[0..31] and the tile's total in word_pref[32].
 __device__ __forceinline__ void tile_prefix(const uint32_t* __restrict__ bitmask, uint32_t block, uint32_t n, uint32_t (&words)[LVL_ITERS],
@@ -74,7 +78,10 @@ __device__ __forceinline__ void assign_tile(uint32_t block, uint32_t base, const
       const uint32_t t = MODE == MODE_NODE ? 0u : tmp[p];
       const uint32_t s = t & IDX_MASK;
       uint32_t flags = t & ~IDX_MASK;
-      if (MODE == MODE_LEAF_DIRECT) {
+      if (MODE == MODE_LEAF_DIRECT && (s & LEAF_SIDE)) {
+        reinterpret_cast<unsigned long long*>(uniq)[rank] = __ldcg(&tab.slots[s & (LEAF_SIDE - 1u)].key);
+        flags &= ~LEAF_SIDE;
+      } else if (MODE == MODE_LEAF_DIRECT) {
         tab.dids[s] = rank;
         reinterpret_cast<unsigned long long*>(uniq)[rank] = leaf_from_2bit(s, S);
       } else if (MODE == MODE_LEAF_HASH) {

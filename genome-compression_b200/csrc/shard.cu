@@ -378,14 +378,19 @@ __global__ void id_base_kernel(const uint32_t* __restrict__ totals, int rank, in
 
 // later occurrences: the finished pointer of the first occurrence lives on its home rank
 __global__ void __launch_bounds__(LVL_THREADS)
-shard_resolve_kernel(const uint32_t* __restrict__ aux, uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ bitmask, PeerHome home,
+shard_resolve_kernel(const uint32_t* aux, uint32_t* __restrict__ out, uint32_t n, const uint32_t* bitmask, PeerHome home,
                      uint64_t ptr_off) {
   const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int it = 0; it < LVL_ITERS; ++it) {
     const uint32_t p = blockIdx.x * LVL_TILE + it * LVL_THREADS + threadIdx.x;
     if (p < n && !((bitmask[p >> 5] >> lane) & 1u)) {
-      const uint32_t t = aux[p], q = t & IDX_MASK;
+      const uint32_t t = aux[p];
+      uint32_t q = t & IDX_MASK;
+      if ((q >> home.log2_positions) == home.self) {  // a run's head (bucket.cu) that is itself a later occurrence: one more hop
+        const uint32_t ql = q & ((1u << home.log2_positions) - 1u);
+        if (ql < p && p - ql < COLLAPSE_WINDOW && !((__ldcg(bitmask + (ql >> 5)) >> (ql & 31u)) & 1u)) q = __ldcg(aux + ql) & IDX_MASK;
+      }
       const uint32_t* first = reinterpret_cast<const uint32_t*>(home.base[q >> home.log2_positions] + ptr_off) + (q & ((1u << home.log2_positions) - 1u));
       out[p] = finish_pointer(__ldcg(first) & IDX_MASK, t & ~IDX_MASK);
     }
@@ -631,7 +636,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     STB_CUDA(s, cudaMemsetAsync(seg_count, 0, 512 * 4, st));
     STB_CUDA(s, cudaMemsetAsync(s.arena + s.off_ans_count, 0, STB_MAX_RANKS * 4, st));
     STB_TRY(shard_partition(s, sb, ptr_cur, (uint32_t)n_cur_local, (uint32_t)n_next_local, (uint32_t)lo, child_first, child_multi, aux, first_bits,
-                            seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
+                            multi_bits, seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
     {
       Launch l(s, "collective_barrier", false);
       STB_TRY(comm.barrier(s));  // every rank's buckets are complete: the owners pull them

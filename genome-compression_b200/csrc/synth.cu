@@ -135,4 +135,34 @@ int synth_genome(Ctx& ctx, char* d_out, uint64_t n_bases, uint64_t first, uint64
   return STB_OK;
 }
 
+// "Real genome" variant of the workload: runs of N (unsequenced stretches) and soft-masked (lower-case)
+// stretches laid over the text, both pure functions of the position.  Per 64 Ki-base block: with
+// probability 8 % one run of 1..16384 N starting in the block's first 48 Ki bases (about 1 % of all
+// bases); per 4 Ki-base block: lower case with probability 1/2.  CPU twin: orc_synth_mask.
+__host__ __device__ __forceinline__ char masked_base(char c, unsigned long long i, unsigned long long seed) {
+  const unsigned long long b = i >> 16;
+  const unsigned long long h = splitmix64(seed ^ 0x4e4e4e4e4e4e4e4eull ^ (b * 0x9E3779B97F4A7C15ull));
+  if (h % 100ull < 8ull) {
+    const unsigned long long start = (b << 16) + ((h >> 8) % 49152ull), len = 1ull + ((h >> 32) % 16384ull);
+    if (i >= start && i < start + len) c = 'N';
+  }
+  const unsigned long long h2 = splitmix64(seed ^ 0x6c6f776572636173ull ^ ((i >> 12) * 0xD1B54A32D192ED03ull));
+  if (h2 & 1ull) c = (char)(c | 0x20);
+  return c;
+}
+
+__global__ void __launch_bounds__(256) synth_mask_kernel(char* __restrict__ text, unsigned long long first, unsigned long long count, unsigned long long seed) {
+  const unsigned long long j = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+  if (j < count) text[j] = masked_base(text[j], first + j, seed);
+}
+
+int synth_mask(Ctx& ctx, char* d_text, uint64_t first, uint64_t count, uint64_t seed) {
+  if (count == 0) return STB_OK;
+  Launch l(ctx, "synth_mask");
+  synth_mask_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, ctx.stream>>>(d_text, first, count, seed);
+  STB_CUDA(ctx, cudaStreamSynchronize(ctx.stream));
+  STB_CUDA(ctx, cudaGetLastError());
+  return STB_OK;
+}
+
 }  // namespace stb

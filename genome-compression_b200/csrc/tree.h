@@ -28,6 +28,7 @@ struct Options {
   uint64_t child_filter = 1;             // exact singleton filter from the child level's bitmaps (node levels >= 1)
   uint64_t locality = 1;                 // slot proportional to a child id above the first node layer
   uint64_t coop_max = 1ull << 20;        // levels with at most this many pointers run in one cooperative launch
+  uint64_t side_table_slots = 1ull << 22; // hash-table slots for leaves outside ACGT next to the direct leaf table (half of them usable)
   uint64_t reserve_pipeline = 1;         // a build also reserves the scratch of sort_tree and decode (the compress path always sorts)
   uint64_t stream_chunk_log2 = 24;       // leaves per chunk of the streaming host build
   uint64_t stream_min_chunks = 4;        // smaller host inputs are copied and built in one shot
@@ -129,6 +130,8 @@ int random_access(const Tree& t, const unsigned long long* d_index, uint64_t q, 
 // synth.cu -------------------------------------------------------------------------
 int synth_genome(Ctx& ctx, char* d_out, uint64_t n_bases, uint64_t first, uint64_t count, uint64_t seed,
                  uint32_t repeat_permille);
+
+int synth_mask(Ctx& ctx, char* d_text, uint64_t first, uint64_t count, uint64_t seed);  // N runs + soft-masking over a generated text
 
 // shared error word for unknown symbols: (byte offset << 8) | upper-cased byte
 std::string unknown_symbol_message(int upper_byte);

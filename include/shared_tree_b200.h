@@ -66,7 +66,7 @@ int stb_release_workspace(stb_tree* tree);
 /* Tunables of the build (thresholds between its code paths).  Defaults are the
  * measured optimum; tests lower them to push small inputs through the large-input paths.
  * Names: "bucket_min", "bucket_levels", "bucket_cap", "partition_threads", "dedup_threads", "bucket_slack_permille", "child_filter", "locality",
- * "coop_max", "reserve_pipeline", "stream_chunk_log2", "stream_min_chunks".  Unknown name: STB_ERR_INVALID_ARG. */
+ * "coop_max", "reserve_pipeline", "side_table_slots", "stream_chunk_log2", "stream_min_chunks".  Unknown name: STB_ERR_INVALID_ARG. */
 int stb_set_option(stb_tree* tree, const char* name, uint64_t value);
 int stb_get_option(const stb_tree* tree, const char* name, uint64_t* value);
 
@@ -152,6 +152,10 @@ int stb_profile_read(stb_tree* tree, const char** names, double* total_ms, uint6
  * genome (n_bases, seed, repeat_permille): i.i.d. ACGT plus planted repeats. */
 int stb_synth_genome(int device, void* cuda_stream, char* out_device, uint64_t n_bases, uint64_t first,
                      uint64_t count, uint64_t seed, uint32_t repeat_permille);
+
+/* The "real genome" variant: lays runs of N (about 1 % of the bases) and soft-masked lower-case stretches over
+ * bases [first, first+count) of a generated text in device memory (a pure function of the position). */
+int stb_synth_mask(int device, void* cuda_stream, char* text_device, uint64_t first, uint64_t count, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -730,3 +730,20 @@ void orc_synth_fill(char* out, uint64_t first, uint64_t count, uint64_t seed, co
     out[j] = acgt[code];
   }
 }
+
+/* "Real genome" variant of the synthetic workload (this repo's own definition; device twin:
+ * csrc/synth.cu masked_base): runs of N and soft-masked (lower-case) stretches, pure functions of the position. */
+void orc_synth_mask(char* text, uint64_t first, uint64_t count, uint64_t seed) {
+  for (uint64_t j = 0; j < count; ++j) {
+    const uint64_t i = first + j, b = i >> 16;
+    const uint64_t h = splitmix(seed ^ 0x4e4e4e4e4e4e4e4eull ^ (b * 0x9E3779B97F4A7C15ull));
+    char c = text[j];
+    if (h % 100ull < 8ull) {
+      const uint64_t start = (b << 16) + ((h >> 8) % 49152ull), len = 1ull + ((h >> 32) % 16384ull);
+      if (i >= start && i < start + len) c = 'N';
+    }
+    const uint64_t h2 = splitmix(seed ^ 0x6c6f776572636173ull ^ ((i >> 12) * 0xD1B54A32D192ED03ull));
+    if (h2 & 1ull) c = (char)(c | 0x20);
+    text[j] = c;
+  }
+}

@@ -103,6 +103,7 @@ typedef struct orc_repeat {
 } orc_repeat;
 uint64_t orc_synth_repeats(uint64_t n_bases, uint64_t seed, uint32_t repeat_permille,
                            orc_repeat* out, uint64_t cap);
+void orc_synth_mask(char* text, uint64_t first, uint64_t count, uint64_t seed);
 void orc_synth_fill(char* out, uint64_t first, uint64_t count, uint64_t seed,
                     const orc_repeat* reps, uint64_t n_reps);
 

@@ -152,6 +152,8 @@ class Oracle:
         L.orc_synth_repeats.restype = C.c_uint64
         L.orc_synth_repeats.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64]
         L.orc_synth_fill.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.orc_synth_mask.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint64]
+        L.orc_synth_mask.restype = None
 
     # ---- primitives ----
     def pack(self, text: bytes, S: int):
@@ -280,6 +282,12 @@ class Oracle:
         out = np.zeros(count, dtype=np.uint8)
         self.lib.orc_synth_fill(out, first, count, seed, reps.ctypes.data if len(reps) else None, len(reps))
         return out
+
+
+    def synth_mask(self, text, first, seed):
+        """In place: N runs and soft-masking over bases [first, first + len(text)) (orc_synth_mask)."""
+        self.lib.orc_synth_mask(text, first, len(text), seed)
+        return text
 
 
 class Ref:

@@ -20,6 +20,7 @@ from oracle.pyoracle import Oracle  # noqa: E402
 def main():
     import torch
     stb, oracle = load_package(), Oracle()
+    pkg = stb
     options = dict(a.split("=") for a in sys.argv[1:])
 
     class Tree(stb.SharedTree):
@@ -89,6 +90,40 @@ def main():
     text[600_001] = ord("N")
     lv = oracle.fasta_to_leaves(bytes(text), 12)
     assert stb.SharedTree(12).build_from_body(bytes(text)).serialize() == oracle.build(lv, 12).serialize()
+    # the "real genome" variant: N runs (leaves outside ACGT go to the side table next to the direct one; runs
+    # of equal nodes collapse before the on-chip dedup) and soft-masked lower case, from device and host memory
+    masked = buf.clone()
+    pkg.synth_mask(masked, seed=11)
+    mtext = masked.cpu().numpy().tobytes()
+    assert mtext.count(b"N") + mtext.count(b"n") > 1000 and any(c in mtext for c in b"acgt")
+    lv = oracle.fasta_to_leaves(mtext, 12)
+    want = oracle.build(lv, 12)
+    for entry, arg in (("device", masked), ("host", mtext)):
+        got = stb.SharedTree(12).build_from_body(arg)
+        assert got.layer_counts() == want.layer_counts(), ("masked", entry)
+        assert got.serialize() == want.serialize(), ("masked", entry)
+        assert np.array_equal(got.decode(), lv), ("masked", entry)
+    # a side table that fills up (512 usable slots, thousands of distinct leaves with IUPAC codes): the hashed leaf level takes over
+    tiny = stb.SharedTree(12).set_option("side_table_slots", 1)
+    iupac = bytearray(mtext[:2_400_000])
+    spots = np.random.default_rng(3).integers(0, len(iupac), 6000)
+    for at, code in zip(spots, b"RYKMSWBDHVN" * 600):
+        iupac[at] = code
+    iupac = bytes(iupac)
+    want_iupac = oracle.build(oracle.fasta_to_leaves(iupac, 12), 12).serialize()
+    assert tiny.build_from_body(torch.frombuffer(bytearray(iupac), dtype=torch.uint8).cuda()).serialize() == want_iupac, "side table overflow"
+    assert tiny.build_from_body(iupac).serialize() == want_iupac, "side table overflow, host"
+    assert stb.SharedTree(12).build_from_body(iupac).serialize() == want_iupac, "IUPAC leaves in the side table, host"
+    # long runs of one letter and of short periods between random stretches (every run longer than a partition tile)
+    rnd = buf[:600_000].cpu().numpy().tobytes()
+    runs = rnd[:240_000] + b"A" * 480_000 + rnd[240_000:360_000] + b"ACGTTGCA" * 90_000 + b"N" * 300_000 + rnd[360_000:] + b"T" * 120_007
+    for S in (12, 4):
+        lvS = oracle.fasta_to_leaves(runs, S)
+        wantS = oracle.build(lvS, S)
+        for entry, arg in (("device", torch.frombuffer(bytearray(runs), dtype=torch.uint8).cuda()), ("host", runs)):
+            got = stb.SharedTree(S).build_from_body(arg)
+            assert got.layer_counts() == wantS.layer_counts(), ("runs", S, entry)
+            assert got.serialize() == wantS.serialize(), ("runs", S, entry)
     rng = np.random.default_rng(5)
     codes = np.array([1, 2, 4, 8, 3, 12, 7, 14, 0, 9, 5, 11, 13, 10, 6, 15], dtype=np.uint64)
     nib = codes[rng.integers(0, 16, size=(40000, 12))]

@@ -219,6 +219,14 @@ def test_synthetic_matches_oracle_generator(stb, oracle):
     reps = oracle.synth_repeats(n, 42, 500)
     covered = int(reps["len"].sum())
     assert 0.35 * n < covered < 0.65 * n
+    # the "real genome" variant (N runs + soft-masking): device and CPU twins agree, whole and in parts
+    stb.synth_mask(buf, seed=42)
+    masked = oracle.synth_mask(want.copy(), 0, 42)
+    assert np.array_equal(buf.cpu().numpy(), masked)
+    stb.synth_mask(part, first=1_234_567, seed=42)
+    assert np.array_equal(part.cpu().numpy(), masked[1_234_567:1_234_567 + 100_001])
+    frac_n = float((masked == ord("N")).sum() + (masked == ord("n")).sum()) / n
+    assert 0.002 < frac_n < 0.03 and 0.3 < float((masked >= ord("a")).sum()) / n < 0.7
 
 
 def test_synthetic_tree_parity(stb, oracle):
@@ -240,11 +248,13 @@ def test_synthetic_tree_parity(stb, oracle):
 def _synth_record(name):
     import json
     from conftest import GOLD
-    return json.loads((GOLD / "synth.json").read_text())[name]
+    return json.loads((GOLD / "synth.json").read_text()).get(name)
 
 
 @pytest.mark.parametrize("name,entry", [("mid_50mbp", "device"), ("mid_50mbp", "host"), ("large_260mbp", "device"),
-                                        ("large_260mbp", "host"), ("config3_3100mbp", "device"), ("config3_3100mbp", "host")])
+                                        ("large_260mbp", "host"), ("config3_3100mbp", "device"), ("config3_3100mbp", "host"),
+                                        ("largeN_260mbp", "device"), ("largeN_260mbp", "host"),
+                                        ("config3N_3100mbp", "device"), ("config3N_3100mbp", "host")])
 def test_synth_reference_golden(stb, name, entry):
     """BASELINE.json configs 3 / 5 at FULL size against the UNMODIFIED reference: tests/golden/synth.json holds
     what oracle/_ref produced for the same generated text (oracle/gen_golden_synth.py): per-layer node counts,
@@ -252,12 +262,16 @@ def test_synth_reference_golden(stb, name, entry):
     (compress.cpp:183-200, src/shared_tree.cpp:488-513) and of the operator[] answers (:268-291)."""
     import torch
     rec = _synth_record(name)
+    if rec is None:
+        pytest.skip(f"tests/golden/synth.json has no record {name} (oracle/gen_golden_synth.py {name})")
     n = rec["bases"]
     free, _ = torch.cuda.mem_get_info()
     if free < 14 * n + (4 << 30):
         pytest.skip("not enough free device memory for this size")
     buf = torch.empty(n, dtype=torch.uint8, device="cuda")
     stb.synth_genome(buf, n, seed=rec["seed"], repeat_permille=rec["repeat_permille"])
+    if rec["variant"] == "nruns":  # N runs (1 % of the bases) and soft-masked lower case: a real assembly's shape
+        stb.synth_mask(buf, seed=rec["seed"])
     tree = stb.SharedTree(12)
     if entry == "host":  # stb_build_from_body(STB_HOST): the chunked build behind the copy
         host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
