@@ -661,7 +661,7 @@ def run_b200_dist(args, world, rank, local_rank):
     if os.environ.get("STB_RANK_PROFILES"):  # per-rank kernel classes, for finding the rank the others wait for
         out_dir = ROOT / "gpurun_out"
         out_dir.mkdir(exist_ok=True)
-        (out_dir / f"rank_profile_n{world}_r{rank}.json").write_text(json.dumps(
+        (out_dir / f"rank_profile_{os.environ['STB_RANK_PROFILES']}_n{world}_r{rank}.json").write_text(json.dumps(
             {k: round(v["ms"] / args.steps, 4) for k, v in prof.items()}))
     ms_per_step = float(ms.item()) / args.steps
     bases_used = n_leaves * DNA

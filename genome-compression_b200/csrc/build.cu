@@ -659,7 +659,9 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     sc.tags_cleared = true;
     sc.serial = 0;
   }
+  const int level_tag0 = t.profile_level;  // the caller's level of `cur` (leaf pointers: 0), or -1
   do {
+    if (level_tag0 >= 0) t.profile_level = level_tag0 + level + 1;
     if (n_cur <= SMALL_MAX) {  // the rest of the tree in one launch
       SmallOut out{};
       int extra = 0;
@@ -753,6 +755,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     n_cur = n_next;
     ++level;
   } while (n_cur > 1);
+  t.profile_level = level_tag0;
   *levels_out = level;
   *root_buf = cur;
   return STB_OK;
@@ -830,6 +833,7 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   }
 
   // ---- leaf level ----
+  t.profile_level = t.opt.profile_levels ? 0 : -1;
   const uint64_t direct_entries = direct ? (1ull << (2 * S)) : 0;
   const uint32_t leaf_cap = direct ? 0u : table_cap(n0);
   if (!direct) {
@@ -883,6 +887,7 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
   uint32_t* cur = nullptr;
   STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n0, sc.counts.ptr + 1, &level, &cur));
   // `cur` now holds the single root pointer.
+  t.profile_level = -1;
 
   return finish_build(t, sc, n0, level, cur, direct);
 }

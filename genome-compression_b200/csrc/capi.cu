@@ -26,10 +26,11 @@ void Ctx::flush_profile() {
   for (auto& p : pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
-      auto it = acc.find(p.name);
+      const std::string name = p.level >= 0 ? std::string(p.name) + "@L" + std::to_string(p.level) : std::string(p.name);
+      auto it = acc.find(name);
       if (it == acc.end()) {
-        acc_order.push_back(p.name);
-        it = acc.emplace(p.name, Acc{}).first;
+        acc_order.push_back(name);
+        it = acc.emplace(name, Acc{}).first;
       }
       it->second.ms += ms;
       it->second.launches += 1;
@@ -144,7 +145,7 @@ int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream) {
 static uint64_t* option_slot(Options& o, const char* name) {
   const struct { const char* name; uint64_t* slot; } table[] = {
       {"bucket_min", &o.bucket_min}, {"bucket_levels", &o.bucket_levels}, {"bucket_cap", &o.bucket_cap}, {"partition_threads", &o.partition_threads}, {"dedup_threads", &o.dedup_threads}, {"bucket_slack_permille", &o.bucket_slack_permille},
-      {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max}, {"reserve_pipeline", &o.reserve_pipeline}, {"side_table_slots", &o.side_table_slots},
+      {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max}, {"reserve_pipeline", &o.reserve_pipeline}, {"side_table_slots", &o.side_table_slots}, {"profile_levels", &o.profile_levels},
       {"stream_chunk_log2", &o.stream_chunk_log2}, {"stream_min_chunks", &o.stream_min_chunks}};
   for (const auto& e : table)
     if (std::strcmp(e.name, name) == 0) return e.slot;

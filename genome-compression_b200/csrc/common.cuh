@@ -325,8 +325,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   mutable std::string error;
   bool profiling = false;
+  int profile_level = -1;  // >= 0: launches are accounted per level ("name@L<level>"; option profile_levels)
 
-  struct Pending { const char* name; cudaEvent_t a, b; };
+  struct Pending { const char* name; cudaEvent_t a, b; int level; };
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
   struct Acc { double ms = 0; uint64_t launches = 0; };
@@ -357,6 +358,7 @@ struct Launch {
     if (kernel) ++g_kernel_launches;
     if (ctx.profiling) {
       p.name = name;
+      p.level = ctx.profile_level;
       p.a = ctx.get_event();
       p.b = ctx.get_event();
       cudaEventRecord(p.a, ctx.stream);

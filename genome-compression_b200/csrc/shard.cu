@@ -30,6 +30,7 @@
 #include <nccl.h>
 
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -550,6 +551,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   const uint64_t n_local = hi0 - lo0;
   const int L = s.pointer_levels;
 
+  s.profile_level = s.opt.profile_levels ? 0 : -1;
   // ---- leaf level: replicated direct table, all-reduce(min) of the first positions, ids everywhere ----
   const uint64_t entries = 1ull << (2 * S);
   const uint64_t canon_entries = std::max<uint64_t>(entries / 2, 1);  // a canonical code's first nucleotide is A or C (dna.cpp:135-143)
@@ -618,6 +620,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     s.level_range(rank, j + 1, &lo, &hi);
     const uint64_t n_next_local = hi - lo, P = s.shard >> (j + 1), n_total = s.level_total(j + 1);
     const int par = j & 1;
+    if (s.opt.profile_levels) s.profile_level = j + 1;
     uint32_t* first_bits = reinterpret_cast<uint32_t*>(s.arena + s.off_first[par]);
     uint32_t* multi_bits = reinterpret_cast<uint32_t*>(s.arena + s.off_multi[par]);
     uint32_t* aux = reinterpret_cast<uint32_t*>(s.arena + s.off_aux);
@@ -646,6 +649,14 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     {
       Launch l(s, "collective_barrier", false);
       STB_TRY(comm.barrier(s));  // every owner's answer lists are complete: the home ranks pull them
+    }
+    if (s.opt.profile_levels > 1) {  // debugging aid: how many answers this owner keeps for every home rank
+      uint32_t kept[STB_MAX_RANKS];
+      STB_CUDA(s, cudaMemcpyAsync(kept, s.arena + s.off_ans_count, sizeof(kept), cudaMemcpyDeviceToHost, st));
+      STB_CUDA(s, cudaStreamSynchronize(st));
+      std::string line = "[stb shard " + std::to_string(rank) + "/" + std::to_string(world) + " node layer " + std::to_string(j) + "] answers kept per home rank:";
+      for (int r = 0; r < world; ++r) line += " " + std::to_string(kept[r]);
+      fprintf(stderr, "%s\n", line.c_str());
     }
     {
       Launch l(s, "shard_apply");
@@ -688,6 +699,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   }
 
   // ---- the top of the tree on rank 0 ----
+  s.profile_level = s.opt.profile_levels ? L : -1;
   STB_TRY(comm.barrier(s));  // every rank's last pointer array is final
   const uint64_t n_top = s.level_total(L - 1);
   if (rank == 0) {
@@ -708,6 +720,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   }
   STB_TRY(comm.barrier(s));  // rank 0 has read the peers' arrays: the arenas may be reused
 
+  s.profile_level = -1;
   // ---- what the host needs to know, once ----
   s.h_totals.assign((size_t)L * world, 0);
   std::vector<uint32_t> overflowed(world);

@@ -32,6 +32,7 @@ struct Options {
   uint64_t reserve_pipeline = 1;         // a build also reserves the scratch of sort_tree and decode (the compress path always sorts)
   uint64_t stream_chunk_log2 = 24;       // leaves per chunk of the streaming host build
   uint64_t stream_min_chunks = 4;        // smaller host inputs are copied and built in one shot
+  uint64_t profile_levels = 0;           // the kernel timings of stb_profile_read are kept per level ("name@L3")
 };
 
 struct Tree : Ctx {
