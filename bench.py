@@ -543,7 +543,43 @@ def run_b200(args):
                 "value": bases_used / fasta_s / 1e9, "unit": "Gbp/s", "ms": round(fasta_s * 1e3, 2), "h2d_bytes": int(fasta_len),
                 "layout": "one '>' header line, 60-column lines", "vs_bare_body_e2e": round(fasta_s * 1e3 / e2e["ms_per_step"], 3) if e2e else None,
                 "layer_counts_equal": fasta_counts == U[1:], "path": "stb_build_from_fasta(STB_HOST)"}
-            del host, dag_host, text_host, back, fasta_host
+            del fasta_host
+            # ---- the "real genome" variant of config 3: runs of N (1 % of the bases) and soft-masked lower case laid
+            # over the same sequence, built from device and from pinned host memory; its own reference golden
+            gold_n = golden_record(args, "nruns")
+            pkg.synth_mask(text, seed=args.seed, device=local_rank, stream=stream.cuda_stream)
+            host.copy_(text)
+            torch.cuda.synchronize()
+            for _ in range(2):
+                tree.build_from_body(text)
+            nrun_ms, _ = timed(lambda: tree.build_from_body(text), reps=max(1, min(args.steps, 3)))
+            tree.build_from_body(host)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps_f):
+                tree.build_from_body(host)
+                _ = (tree.width(), tree.node_count())
+            torch.cuda.synchronize()
+            nrun_host_s = (time.perf_counter() - t0) / reps_f
+            nrun_counts = tree.layer_counts()
+            tree.sort()
+            nrun_bytes = tree.bytes()
+            tree.serialize_to_host(dag_host)
+            parity["nruns_sha256"] = __import__("hashlib").sha256(dag_host[:nrun_bytes].numpy().tobytes()).hexdigest()
+            parity["nruns_golden"] = gold_n["name"] if gold_n else None
+            pipeline["nruns"] = {
+                "build_ms": round(nrun_ms, 3), "value": bases_used / (nrun_ms * 1e-3) / 1e9, "unit": "Gbp/s",
+                "vs_plain_build": round(nrun_ms / ms_per_step, 3), "e2e_ms": round(nrun_host_s * 1e3, 2),
+                "e2e_value": bases_used / nrun_host_s / 1e9, "vs_bare_body_e2e": round(nrun_host_s * 1e3 / e2e["ms_per_step"], 3) if e2e else None,
+                "layout": "N runs of 1..16384 bases in 8 % of the 64 Ki-base blocks, lower case in half of the 4 Ki-base blocks",
+                "stream_bytes": int(nrun_bytes), "path": "stb_build_from_body(DEVICE | HOST)"}
+            if gold_n:
+                check_against_golden(gold_n, "per-layer node counts (N-run variant)", nrun_counts, gold_n["layer_counts"])
+                check_against_golden(gold_n, "stream sha256 after sort_tree (N-run variant)", parity["nruns_sha256"], gold_n["post_sha256"])
+                parity["nruns_equal_to_reference"] = True
+            pkg.synth_genome(text, n_bases, seed=args.seed, repeat_permille=args.repeat_permille, device=local_rank, stream=stream.cuda_stream)
+            tree.build_from_body(text)
+            del host, dag_host, text_host, back
         del dag
         if gold:
             check_against_golden(gold, "per-layer node counts", parity["layer_counts"], gold["layer_counts"])

@@ -53,15 +53,19 @@ __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key
 // segment of (bucket, source) is read from the source's memory over NVLink with the same coalesced
 // loads a local segment gets (blockIdx.y = local bucket * world + source).  Nothing is pushed:
 // small scattered stores over NVLink ran at a quarter of the rate of these reads.
-template <bool FROM_CHILDREN, int PT_THREADS, bool PEER>
-__global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
-partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
-                 const unsigned long long* in_keys, const uint32_t* in_pos,
-                 const uint32_t* __restrict__ in_count, uint32_t in_cap,
-                 unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
-                 uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
-                 uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
-                 uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, PeerDest peer) {
+// EXACT (the second pass again, after a final bucket outgrew its fixed region: a key with thousands of
+// occurrences, e.g. the node of two all-N leaves once per N run): the first attempt has counted every final
+// bucket exactly (the counter is bumped before the capacity check), so the records are scattered again into
+// regions of exactly those sizes (exact_off = exclusive scan of the counts, exact_cursor = fill state).
+template <bool FROM_CHILDREN, int PT_THREADS, bool PEER, bool EXACT>
+__device__ __forceinline__ void
+partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
+               const unsigned long long* in_keys, const uint32_t* in_pos,
+               const uint32_t* __restrict__ in_count, uint32_t in_cap,
+               unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
+               uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
+               uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
+               uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, const PeerDest& peer, const uint32_t* __restrict__ exact_off) {
   constexpr int PT_TILE = PT_THREADS * PT_ITEMS, PT_WARPS = PT_THREADS / 32;
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
@@ -75,12 +79,12 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nb = 1u << bits;
   uint32_t count;
-  const uint32_t first = blockIdx.x * PT_TILE;
+  const uint32_t first = bx * PT_TILE;
   uint64_t in_base = 0;
   if (FROM_CHILDREN) {
     count = n_next;
   } else if (PEER) {
-    const uint32_t src = blockIdx.y % peer.world, local = blockIdx.y / peer.world;
+    const uint32_t src = by % peer.world, local = by / peer.world;
     const uint32_t bucket = (peer.src << peer.bucket_shift) | local;  // this owner's bucket, in the source's numbering
     count = min(*reinterpret_cast<const volatile uint32_t*>(peer.base[src] + peer.count_off + 4ull * bucket), in_cap);
     if (first >= count) return;
@@ -88,9 +92,9 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     in_pos = reinterpret_cast<const uint32_t*>(peer.base[src] + peer.pos_off);
     in_base = (uint64_t)bucket * in_cap;
   } else {
-    count = min(__ldg(in_count + blockIdx.y), in_cap);
+    count = min(__ldg(in_count + by), in_cap);
     if (first >= count) return;
-    in_base = (uint64_t)blockIdx.y * in_cap;
+    in_base = (uint64_t)by * in_cap;
   }
   for (uint32_t i = tid; i < nb; i += PT_THREADS) hist[i] = 0;
   __syncthreads();
@@ -198,9 +202,10 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
       loff[tid] = before + x - c;
       uint32_t g = 0;
       if (c) {
-        const uint32_t bucket = FROM_CHILDREN ? tid : (((blockIdx.y / segs) << bits) | tid);
-        g = atomicAdd(out_count + bucket, c);
-        if (g + c > out_cap) *overflow = 1u;
+        const uint32_t bucket = FROM_CHILDREN ? tid : (((by / segs) << bits) | tid);
+        g = atomicAdd(out_count + bucket, c);  // EXACT: out_count is the fill state of the exact-size regions
+        if (EXACT) g += __ldg(exact_off + bucket);
+        else if (g + c > out_cap) *overflow = 1u;
       }
       goff[tid] = g;
     }
@@ -224,13 +229,83 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
     if (j < staged) {
       const uint32_t d = sdig[j];
       const uint32_t at = goff[d] + (j - loff[d]);  // place in the bucket's region
-      if (at < out_cap) {
-        const uint32_t bucket = FROM_CHILDREN ? d : (((blockIdx.y / segs) << bits) | d);
+      if (EXACT) {
+        out_keys[at] = skey[j];
+        out_pos[at] = spos[j];
+      } else if (at < out_cap) {
+        const uint32_t bucket = FROM_CHILDREN ? d : (((by / segs) << bits) | d);
         const uint64_t dst = (uint64_t)bucket * out_cap + at;
         out_keys[dst] = skey[j];
         out_pos[dst] = spos[j];
       }
     }
+  }
+}
+
+template <bool FROM_CHILDREN, int PT_THREADS, bool PEER>
+__global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
+partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
+                 const unsigned long long* in_keys, const uint32_t* in_pos,
+                 const uint32_t* __restrict__ in_count, uint32_t in_cap,
+                 unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
+                 uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
+                 uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
+                 uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, PeerDest peer) {
+  partition_tile<FROM_CHILDREN, PT_THREADS, PEER, false>(blockIdx.x, blockIdx.y, cur, n_cur, n_next, in_keys, in_pos, in_count, in_cap, out_keys, out_pos,
+                                                         out_count, out_cap, shift, bits, aux, first_bits, multi_bits, child_first, child_multi, overflow,
+                                                         segs, pos_base, peer, nullptr);
+}
+
+// overflow[0]: the level cannot be deduplicated on chip (a first-pass bucket outgrew its region, or a final
+// bucket holds more distinct keys than the shared-memory table) - build.cu re-runs it through the table in
+// HBM.  overflow[1]: a final bucket outgrew its fixed region - the three kernels below take over.
+__device__ __forceinline__ bool exact_pass_wanted(const uint32_t* overflow) { return overflow[1] != 0u && overflow[0] == 0u; }
+
+// exclusive scan of the final buckets' exact record counts; clears the counts (they become the fill state)
+__global__ void __launch_bounds__(1024) exact_offsets_kernel(uint32_t* __restrict__ count2, uint32_t nb, uint32_t* __restrict__ off,
+                                                              const uint32_t* __restrict__ overflow) {
+  if (!exact_pass_wanted(overflow)) return;
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0u;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 < nb; i0 += 1024) {
+    const uint32_t i = i0 + tid;
+    const uint32_t c = i < nb ? count2[i] : 0u;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    uint32_t before = carry;
+    for (uint32_t w = 0; w < warp; ++w) before += warp_sum[w];
+    if (i < nb) {
+      off[i] = before + x - c;
+      count2[i] = 0u;
+    }
+    __syncthreads();
+    if (tid == 1023) carry = before + x;
+    __syncthreads();
+  }
+  if (tid == 0) off[nb] = carry;
+}
+
+// the second pass again, into the exact-size regions; a grid that fits the machine walks the tiles, so the
+// launch costs next to nothing when it has nothing to do
+template <int PT_THREADS>
+__global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
+partition_exact_kernel(const unsigned long long* in_keys, const uint32_t* in_pos, const uint32_t* __restrict__ in_count, uint32_t in_cap,
+                       unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ fill, int shift, int bits,
+                       uint32_t* __restrict__ overflow, const uint32_t* __restrict__ exact_off, uint32_t tiles_x, uint32_t tiles_y) {
+  if (!exact_pass_wanted(overflow)) return;
+  for (uint32_t v = blockIdx.x; v < tiles_x * tiles_y; v += gridDim.x) {
+    partition_tile<false, PT_THREADS, false, true>(v % tiles_x, v / tiles_x, nullptr, 0u, 0u, in_keys, in_pos, in_count, in_cap, out_keys, out_pos, fill, 0u,
+                                                   shift, bits, nullptr, nullptr, nullptr, nullptr, nullptr, overflow, 1u, 0u, PeerDest{}, exact_off);
+    __syncthreads();
   }
 }
 
@@ -253,7 +328,7 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   __shared__ uint32_t tmin_cnt[STB_MAX_RANKS], tmin_base[STB_MAX_RANKS];  // PEER: answers per home rank
   const uint32_t* overflow_out = overflow;
   if (PEER && threadIdx.x < STB_MAX_RANKS) tmin_cnt[threadIdx.x] = 0u;
-  if (*overflow) return;
+  if (overflow[0] || (!PEER && overflow[1])) return;
   const uint32_t tid = threadIdx.x;
   const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
   if (count == 0) return;
@@ -346,6 +421,71 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   }
 }
 
+// The same for final buckets of any size (exact-size regions, see partition_tile): the records are walked
+// twice in chunks instead of being kept in registers.  Thousands of occurrences of one key add records, not
+// table entries; only a bucket with more DISTINCT keys than the table holds gives up (overflow[0]).
+template <int DD_THREADS>
+__global__ void __launch_bounds__(DD_THREADS)
+bucket_dedup_chunked_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ off, uint32_t nb,
+                            uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits, uint32_t* __restrict__ overflow) {
+  if (!exact_pass_wanted(overflow)) return;
+  extern __shared__ __align__(16) uint8_t smem[];
+  unsigned long long* tkey = reinterpret_cast<unsigned long long*>(smem);
+  uint32_t* tmin = reinterpret_cast<uint32_t*>(smem + (size_t)DD_SLOTS * 8);
+  uint32_t* tmulti = tmin + DD_SLOTS;
+  __shared__ uint32_t full;
+  const uint32_t tid = threadIdx.x;
+  constexpr uint32_t mask = DD_SLOTS - 1;
+  for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+    const uint32_t base = __ldg(off + b), count = __ldg(off + b + 1) - base;
+    if (count == 0) continue;
+    for (uint32_t i = tid; i < DD_SLOTS; i += DD_THREADS) {
+      tkey[i] = EMPTY_KEY;
+      tmin[i] = 0xffffffffu;
+    }
+    if (tid < DD_SLOTS / 32) tmulti[tid] = 0u;
+    if (tid == 0) full = 0u;
+    __syncthreads();
+    for (uint32_t i = tid; i < count; i += DD_THREADS) {
+      const unsigned long long key = __ldg(keys + base + i);
+      const uint32_t pos = __ldg(poss + base + i);
+      uint32_t h = (uint32_t)bucket_hash(key) & mask, steps = 0;
+      for (;;) {
+        unsigned long long k = tkey[h];
+        if (k == EMPTY_KEY) k = atomicCAS(&tkey[h], EMPTY_KEY, key);
+        if (k == EMPTY_KEY) break;  // claimed
+        if (k == key) {
+          if (!((tmulti[h >> 5] >> (h & 31)) & 1u)) atomicOr(&tmulti[h >> 5], 1u << (h & 31));
+          break;
+        }
+        h = (h + 1) & mask;
+        if (++steps == DD_SLOTS) break;  // every slot holds another key
+      }
+      if (steps == DD_SLOTS) full = 1u;
+      else if (tmin[h] > pos) atomicMin(&tmin[h], pos);
+    }
+    __syncthreads();
+    if (full) {
+      if (tid == 0) overflow[0] = 1u;
+      return;  // the whole level is done again through the table in HBM
+    }
+    for (uint32_t i = tid; i < count; i += DD_THREADS) {
+      const unsigned long long key = __ldg(keys + base + i);
+      const uint32_t p = __ldg(poss + base + i);
+      uint32_t h = (uint32_t)bucket_hash(key) & mask;
+      while (tkey[h] != key) h = (h + 1) & mask;
+      const uint32_t fp = tmin[h];
+      if (fp != p) {  // a later occurrence: not a first, and it points at the first
+        atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
+        atomicOr(aux + p, fp);
+      } else if ((tmulti[h >> 5] >> (h & 31)) & 1u) {
+        atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 BucketPlan bucket_plan(uint64_t n, const Options& opt) {
@@ -358,7 +498,7 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt) {
   pl.b1 = (bits + 1) / 2;
   pl.b2 = bits - pl.b1;
   const uint64_t mean1 = ceil_div(n, 1ull << pl.b1);
-  pl.cap1 = (uint32_t)((mean1 + mean1 * opt.bucket_slack_permille / 1000 + 1024 + 3) & ~3ull);
+  pl.cap1 = (uint32_t)((mean1 + mean1 * opt.bucket_slack_permille / 1000 + opt.bucket_headroom + 3) & ~3ull);
   pl.usable = (n >> bits) <= (uint64_t)pl.cap2 * 2 / 3 && n < (1ull << 29);
   pl.partition_threads = (int)opt.partition_threads;
   pl.dedup_threads = (int)opt.dedup_threads;
@@ -384,9 +524,27 @@ static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl
     Launch l(ctx, "bucket_partition");
     const dim3 grid((unsigned)ceil_div(pl.cap1, TILE), 1u << pl.b1);
     partition_kernel<false, T, false><<<grid, T, smem, st>>>(nullptr, 0u, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr, ws.pos2.ptr,
-                                                             count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, nullptr, overflow,
+                                                             count2, pl.cap2, 64 - pl.b1 - pl.b2, pl.b2, nullptr, nullptr, nullptr, nullptr, nullptr, overflow + 1,
                                                              1u, 0u, PeerDest{});
   }
+  return STB_OK;
+}
+
+// What runs when a final bucket outgrew its region (device-side decision: all three return at once otherwise).
+template <int T, int D>
+static int launch_exact_pass(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, uint32_t nb, const uint32_t* count1, uint32_t* count2, uint32_t* exact_off,
+                             uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t* overflow) {
+  cudaStream_t st = ctx.stream;
+  const size_t smem = pt_smem(T);
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_exact_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_chunked_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  Launch l(ctx, "bucket_exact");
+  exact_offsets_kernel<<<1, 1024, 0, st>>>(count2, nb, exact_off, overflow);
+  const uint32_t tiles_x = (uint32_t)ceil_div(pl.cap1, T * PT_ITEMS), tiles_y = 1u << pl.b1;
+  partition_exact_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)tiles_x * tiles_y, 148 * (2048 / T)), T, smem, st>>>(
+      ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr, ws.pos2.ptr, count2, 64 - pl.b1 - pl.b2, pl.b2, overflow, exact_off, tiles_x, tiles_y);
+  bucket_dedup_chunked_kernel<D><<<std::min<uint32_t>(nb, 148 * 4), D, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, exact_off, nb, aux, first_bits, multi_bits,
+                                                                                      overflow);
   return STB_OK;
 }
 
@@ -449,7 +607,8 @@ int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl) {
   STB_CUDA(ctx, ws.pos1.ensure(r1, st));
   STB_CUDA(ctx, ws.keys2.ensure(r2, st));
   STB_CUDA(ctx, ws.pos2.ensure(r2, st));
-  STB_CUDA(ctx, ws.counters.ensure((1ull << pl.b1) + (1ull << (pl.b1 + pl.b2)) + 1, st));
+  // counts of both passes, the two overflow words, the exact-size offsets (one more than there are final buckets)
+  STB_CUDA(ctx, ws.counters.ensure((1ull << pl.b1) + 2 * (1ull << (pl.b1 + pl.b2)) + 4, st));
   return STB_OK;
 }
 
@@ -461,8 +620,9 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, cons
   const uint32_t nb1 = 1u << pl.b1, nb = 1u << (pl.b1 + pl.b2);
   uint32_t* count1 = ws.counters.ptr;
   uint32_t* count2 = count1 + nb1;
-  uint32_t* overflow = count2 + nb;
-  STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 1) * 4, st));
+  uint32_t* overflow = count2 + nb;  // two words (see exact_pass_wanted)
+  uint32_t* exact_off = overflow + 2;
+  STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 2) * 4, st));
   if (pl.partition_threads == 512)
     STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow));
   else
@@ -470,6 +630,8 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, cons
   if (pl.dedup_threads == 256) STB_TRY(launch_dedup<256>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else if (pl.dedup_threads == 512) STB_TRY(launch_dedup<512>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else STB_TRY(launch_dedup<1024>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
+  if (pl.partition_threads == 512) STB_TRY((launch_exact_pass<512, 512>(ctx, ws, pl, nb, count1, count2, exact_off, aux, first_bits, multi_bits, overflow)));
+  else STB_TRY((launch_exact_pass<1024, 512>(ctx, ws, pl, nb, count1, count2, exact_off, aux, first_bits, multi_bits, overflow)));
   *overflow_out = overflow;
   return STB_OK;
 }

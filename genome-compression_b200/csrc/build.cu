@@ -314,7 +314,8 @@ resolve_kernel(const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, c
           uint32_t q = s;
           if (!firstpos) {
             q = __ldcg(&tab.slots[s].minpos);
-            if (multi_bits) atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
+            // test before set: the positions of an N run (or of any long run) all name the same first occurrence
+            if (multi_bits && !((__ldcg(multi_bits + (q >> 5)) >> (q & 31u)) & 1u)) atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
           } else if (p - q < COLLAPSE_WINDOW && !((__ldcg(bitmask + (q >> 5)) >> (q & 31u)) & 1u)) {
             // p repeats its predecessor and q is the head of its run (bucket.cu), itself a later occurrence
             q = __ldcg(aux + q) & IDX_MASK;
@@ -500,7 +501,7 @@ mid_levels_kernel(uint32_t* buf_a, uint32_t* buf_b, uint32_t n_cur, MidLevels ou
         if (p < n_next && !((first_bits[p >> 5] >> lane) & 1u)) {
           const uint32_t t = aux[p];
           const uint32_t q = __ldcg(&tab.slots[t & IDX_MASK].minpos);
-          atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
+          if (!((__ldcg(multi_bits + (q >> 5)) >> (q & 31u)) & 1u)) atomicOr(multi_bits + (q >> 5), 1u << (q & 31));
           nxt[p] = finish_pointer(__ldcg(nxt + q) & IDX_MASK, t & ~IDX_MASK);
         }
       }

@@ -144,7 +144,7 @@ int stb_create(stb_tree** out, int device, int dna_size, void* cuda_stream) {
 
 static uint64_t* option_slot(Options& o, const char* name) {
   const struct { const char* name; uint64_t* slot; } table[] = {
-      {"bucket_min", &o.bucket_min}, {"bucket_levels", &o.bucket_levels}, {"bucket_cap", &o.bucket_cap}, {"partition_threads", &o.partition_threads}, {"dedup_threads", &o.dedup_threads}, {"bucket_slack_permille", &o.bucket_slack_permille},
+      {"bucket_min", &o.bucket_min}, {"bucket_levels", &o.bucket_levels}, {"bucket_cap", &o.bucket_cap}, {"partition_threads", &o.partition_threads}, {"dedup_threads", &o.dedup_threads}, {"bucket_slack_permille", &o.bucket_slack_permille}, {"bucket_headroom", &o.bucket_headroom},
       {"child_filter", &o.child_filter}, {"locality", &o.locality}, {"coop_max", &o.coop_max}, {"reserve_pipeline", &o.reserve_pipeline}, {"side_table_slots", &o.side_table_slots}, {"profile_levels", &o.profile_levels},
       {"stream_chunk_log2", &o.stream_chunk_log2}, {"stream_min_chunks", &o.stream_min_chunks}};
   for (const auto& e : table)
@@ -422,10 +422,12 @@ int stb_serialize(const stb_tree* tree, uint8_t* out, uint64_t cap, int memory, 
   if (memory == STB_DEVICE && (reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
     STB_TRY(serialize_tree(t, out, cap));
   } else {
-    DevBuf<uint8_t> d;
-    STB_CUDA(t, d.alloc(t.stream_bytes + 16, t.stream));
-    STB_TRY(serialize_tree(t, d.ptr, t.stream_bytes));
-    STB_TRY(from_device(t, out, d.ptr, t.stream_bytes, memory));
+    // through the handle's grow-only staging buffer (the text it held is no longer needed): no 1.7 GB
+    // allocation per call
+    STB_CUDA(t, t.staging.ensure(t.stream_bytes + 16, t.stream));
+    uint8_t* d = reinterpret_cast<uint8_t*>(t.staging.ptr);
+    STB_TRY(serialize_tree(t, d, t.stream_bytes));
+    STB_TRY(from_device(t, out, d, t.stream_bytes, memory));
   }
   if (written) *written = t.stream_bytes;
   return STB_OK;
@@ -455,10 +457,10 @@ int stb_decode_ascii(const stb_tree* tree, uint64_t first, uint64_t count, char*
   STB_TRY(use_device(tree));
   Tree& t = const_cast<stb_tree&>(*tree);
   if (memory == STB_DEVICE) return decode_range(t, first, count, nullptr, out);
-  DevBuf<char> d;
-  STB_CUDA(t, d.alloc(count * (uint64_t)t.S + 16, t.stream));
-  STB_TRY(decode_range(t, first, count, nullptr, d.ptr));
-  return from_device(t, out, d.ptr, count * (uint64_t)t.S, STB_HOST);
+  // through the handle's grow-only staging buffer: no allocation of the text's size per call
+  STB_CUDA(t, t.staging.ensure(count * (uint64_t)t.S + 16, t.stream));
+  STB_TRY(decode_range(t, first, count, nullptr, t.staging.ptr));
+  return from_device(t, out, t.staging.ptr, count * (uint64_t)t.S, STB_HOST);
 }
 
 int stb_random_access(const stb_tree* tree, const uint64_t* index, uint64_t queries, uint64_t* out, int memory) {

@@ -246,13 +246,245 @@ int serialize_tree(Tree& t, uint8_t* d_out, uint64_t cap) {
   return STB_OK;
 }
 
-// Host-side parse of the variable-length stream (inherently sequential: every
-// pointer's length is known only from its first byte), then one upload per layer.
-// shared_tree::deserialize, src/shared_tree.cpp:520-538; pointers come back with
-// invariant = false (:162).
+// ---- deserialize: the variable-length stream parsed on the device ----------------------------------
+// A pointer's length is known only from its first byte, so where the pointers of a layer start looks
+// sequential.  It is a 4-state automaton, though: seen from a 32-byte chunk, the only unknown is
+// where the first pointer of the chunk starts (offset 0..3: a pointer spans at most 4 bytes), and every
+// entry offset maps to an exit offset into the next chunk and a number of pointers.  Such maps compose
+// associatively, so: pass 1 reduces every 8 KiB tile to its map, one CTA scans the tile maps (which also
+// numbers the pointers), pass 2 walks every chunk from its now known entry, decodes the pointers and
+// writes them out by number.  A layer's byte length is not in the stream (only its node count), so a
+// layer is parsed over the longest extent it could have (8 bytes per node) and the thread that decodes
+// its last pointer reports where the layer really ends; the host reads that number and goes on.
+constexpr int DP_THREADS = 256;
+constexpr int DP_CHUNK = 32;                      // bytes per thread
+constexpr int DP_TILE = DP_THREADS * DP_CHUNK;    // bytes per CTA
+constexpr uint64_t DP_SMALL = 2048;               // layers of at most this many nodes are parsed on the host
+
+struct ParseMap {
+  uint32_t exits;   // 2 bits per entry offset: the offset at which the next chunk's first pointer starts
+  uint32_t cnt[4];  // pointers that start inside, per entry offset
+};
+
+__device__ __forceinline__ uint32_t pick4(const uint32_t (&v)[4], uint32_t i) {
+  return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3]));
+}
+
+// `a` first, then `b`
+__device__ __forceinline__ ParseMap compose(const ParseMap& a, const ParseMap& b) {
+  ParseMap r;
+  r.exits = 0;
+#pragma unroll
+  for (uint32_t e = 0; e < 4; ++e) {
+    const uint32_t x = (a.exits >> (2 * e)) & 3u;
+    r.exits |= ((b.exits >> (2 * x)) & 3u) << (2 * e);
+    r.cnt[e] = a.cnt[e] + pick4(b.cnt, x);
+  }
+  return r;
+}
+
+__device__ __forceinline__ ParseMap shfl_up_map(const ParseMap& m, int d) {
+  ParseMap r;
+  r.exits = __shfl_up_sync(0xffffffffu, m.exits, d);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) r.cnt[e] = __shfl_up_sync(0xffffffffu, m.cnt[e], d);
+  return r;
+}
+
+__device__ __forceinline__ ParseMap identity_map() { return ParseMap{0xE4u, {0u, 0u, 0u, 0u}}; }  // exits[e] = e
+
+// The tile's bytes in shared memory, transposed: word w of thread t's chunk at sw[w * DP_THREADS + t]
+// (a thread walking its chunk then never shares a bank with another), plus the first word after the tile.
+struct TileBytes {
+  uint32_t* sw;
+  __device__ __forceinline__ uint32_t word(uint32_t t, uint32_t w) const {
+    return w < 8u ? sw[w * DP_THREADS + t] : sw[t + 1u < (uint32_t)DP_THREADS ? t + 1u : 8u * DP_THREADS];
+  }
+  __device__ __forceinline__ uint32_t byte(uint32_t t, uint32_t pos) const { return (word(t, pos >> 2) >> (8u * (pos & 3u))) & 0xffu; }
+};
+
+__device__ __forceinline__ void load_tile(const uint8_t* __restrict__ stream, uint64_t tile_begin, uint32_t* sw) {
+  const uint32_t t = threadIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(stream + tile_begin + (uint64_t)t * DP_CHUNK);
+  const uint4 a = __ldg(src), b = __ldg(src + 1);
+  sw[0 * DP_THREADS + t] = a.x; sw[1 * DP_THREADS + t] = a.y; sw[2 * DP_THREADS + t] = a.z; sw[3 * DP_THREADS + t] = a.w;
+  sw[4 * DP_THREADS + t] = b.x; sw[5 * DP_THREADS + t] = b.y; sw[6 * DP_THREADS + t] = b.z; sw[7 * DP_THREADS + t] = b.w;
+  if (t == 0) sw[8 * DP_THREADS] = __ldg(reinterpret_cast<const uint32_t*>(stream + tile_begin + DP_TILE));
+}
+
+// the chunk of thread t as a map; the layer's first chunk starts at `start_off` whatever the entry
+__device__ __forceinline__ ParseMap chunk_map(const TileBytes& tb, uint32_t t, bool first_chunk, uint32_t start_off) {
+  ParseMap m;
+  m.exits = 0;
+#pragma unroll
+  for (uint32_t e = 0; e < 4; ++e) {
+    uint32_t pos = first_chunk ? start_off : e, c = 0;
+    while (pos < (uint32_t)DP_CHUNK) {
+      pos += 1u + (tb.byte(t, pos) >> 6);
+      ++c;
+    }
+    m.exits |= (pos - DP_CHUNK) << (2 * e);
+    m.cnt[e] = c;
+  }
+  return m;
+}
+
+// inclusive scan over the CTA's 256 chunk maps; returns the exclusive map of this thread, the tile's in *tile
+__device__ __forceinline__ ParseMap block_scan_maps(const ParseMap& mine, ParseMap* warp_maps /* shared, 8 */, ParseMap* tile) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ParseMap incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const ParseMap up = shfl_up_map(incl, d);
+    if (lane >= (uint32_t)d) incl = compose(up, incl);
+  }
+  if (lane == 31) warp_maps[warp] = incl;
+  __syncthreads();
+  ParseMap before = identity_map(), total = identity_map();
+  for (uint32_t w = 0; w < DP_THREADS / 32; ++w) {
+    if (w == warp) before = total;
+    total = compose(total, warp_maps[w]);
+  }
+  *tile = total;
+  ParseMap excl = shfl_up_map(incl, 1);
+  if (lane == 0) excl = identity_map();
+  __syncthreads();
+  return compose(before, excl);
+}
+
+__global__ void __launch_bounds__(DP_THREADS)
+parse_tile_maps_kernel(const uint8_t* __restrict__ stream, uint64_t begin, uint32_t start_off, ParseMap* __restrict__ tile_maps) {
+  __shared__ uint32_t sw[8 * DP_THREADS + 1];
+  __shared__ ParseMap warp_maps[DP_THREADS / 32];
+  load_tile(stream, begin + (uint64_t)blockIdx.x * DP_TILE, sw);
+  __syncthreads();
+  const TileBytes tb{sw};
+  const ParseMap mine = chunk_map(tb, threadIdx.x, blockIdx.x == 0 && threadIdx.x == 0, start_off);
+  ParseMap tile;
+  block_scan_maps(mine, warp_maps, &tile);
+  if (threadIdx.x == 0) tile_maps[blockIdx.x] = tile;
+}
+
+// exclusive scan of the tile maps, evaluated at entry offset 0: per tile (entry offset, pointers before it)
+__global__ void __launch_bounds__(1024)
+parse_scan_tiles_kernel(const ParseMap* __restrict__ tile_maps, uint32_t tiles, uint2* __restrict__ tile_entry) {
+  __shared__ ParseMap warp_maps[32];
+  __shared__ uint32_t carry_state;
+  __shared__ unsigned long long carry_cnt;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    carry_state = 0u;
+    carry_cnt = 0ull;
+  }
+  __syncthreads();
+  for (uint32_t base = 0; base < tiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const ParseMap mine = i < tiles ? tile_maps[i] : identity_map();
+    ParseMap incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const ParseMap up = shfl_up_map(incl, d);
+      if (lane >= (uint32_t)d) incl = compose(up, incl);
+    }
+    if (lane == 31) warp_maps[warp] = incl;
+    __syncthreads();
+    ParseMap before = identity_map(), total = identity_map();
+    for (uint32_t w = 0; w < 32; ++w) {
+      if (w == warp) before = total;
+      total = compose(total, warp_maps[w]);
+    }
+    ParseMap excl = shfl_up_map(incl, 1);
+    if (lane == 0) excl = identity_map();
+    excl = compose(before, excl);
+    const uint32_t st = carry_state;
+    const unsigned long long cn = carry_cnt;
+    if (i < tiles) {
+      const unsigned long long prefix = cn + pick4(excl.cnt, st);
+      tile_entry[i] = make_uint2((excl.exits >> (2 * st)) & 3u, (uint32_t)(prefix < 0xffffffffull ? prefix : 0xffffffffull));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      carry_state = (total.exits >> (2 * st)) & 3u;
+      carry_cnt = cn + pick4(total.cnt, st);
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ uint32_t ptr_decode(uint32_t b0, uint32_t rest /* the following bytes, first in the low byte */) {
+  const uint32_t seg = b0 >> 6;
+  uint32_t off = b0 & 0xfu;
+  for (uint32_t b = 0; b < seg; ++b) off = (off << 8) | ((rest >> (8 * b)) & 0xffu);
+  const uint32_t first[4] = {0u, 16u, 4112u, 1052688u};
+  const uint32_t idx = (seg == 3u && off == 0xfffffffu) ? IDX_MASK : pick4(first, seg) + off;
+  return idx | (((b0 >> 4) & 1u) << 29) | (((b0 >> 5) & 1u) << 30);
+}
+
+// result[0] = absolute offset of the byte after the layer's last pointer, result[1] = 1 when a pointer indexes past `below`
+__global__ void __launch_bounds__(DP_THREADS)
+parse_emit_kernel(const uint8_t* __restrict__ stream, uint64_t begin, uint32_t start_off, const uint2* __restrict__ tile_entry,
+                  uint32_t* __restrict__ out, uint32_t n_ptrs, uint32_t below, unsigned long long* __restrict__ result) {
+  __shared__ uint32_t sw[8 * DP_THREADS + 1];
+  __shared__ ParseMap warp_maps[DP_THREADS / 32];
+  __shared__ uint32_t sout[DP_TILE];
+  const uint2 entry = tile_entry[blockIdx.x];
+  if (entry.y >= n_ptrs) return;  // past the layer's end
+  const uint64_t tile_begin = begin + (uint64_t)blockIdx.x * DP_TILE;
+  load_tile(stream, tile_begin, sw);
+  __syncthreads();
+  const TileBytes tb{sw};
+  const uint32_t t = threadIdx.x;
+  const bool first_chunk = blockIdx.x == 0 && t == 0;
+  const ParseMap mine = chunk_map(tb, t, first_chunk, start_off);
+  ParseMap tile;
+  const ParseMap excl = block_scan_maps(mine, warp_maps, &tile);
+  const uint32_t e = (excl.exits >> (2 * entry.x)) & 3u;
+  uint32_t local = pick4(excl.cnt, entry.x);           // pointers of the tile before this chunk
+  const uint32_t tile_total = pick4(tile.cnt, entry.x);
+  uint32_t pos = first_chunk ? start_off : e;
+  bool bad = false;
+  while (pos < (uint32_t)DP_CHUNK) {
+    const uint32_t b0 = tb.byte(t, pos);
+    const uint32_t seg = b0 >> 6;
+    uint32_t rest = 0;
+    for (uint32_t b = 0; b < seg; ++b) rest |= tb.byte(t, pos + 1 + b) << (8 * b);
+    const uint32_t raw = ptr_decode(b0, rest);
+    const uint32_t number = entry.y + local;  // < 2^32: entry.y < n_ptrs <= 2^30, local <= 8192
+    pos += seg + 1u;
+    if (number < n_ptrs) {
+      const uint32_t idx = raw & IDX_MASK;
+      bad |= idx != IDX_MASK && idx >= below;
+      sout[local] = raw;
+      if (number == n_ptrs - 1u) result[0] = tile_begin + (uint64_t)t * DP_CHUNK + pos;
+    }
+    ++local;
+  }
+  if (bad) result[1] = 1ull;
+  __syncthreads();
+  const uint32_t keep = min(tile_total, n_ptrs - entry.y);
+  for (uint32_t i = t; i < keep; i += DP_THREADS) out[entry.y + i] = sout[i];
+}
+
+// leaves: ceil(S/2) bytes each, most significant first (src/dna.cpp:149-161)
+__global__ void __launch_bounds__(256)
+parse_leaves_kernel(const uint8_t* __restrict__ stream, uint64_t begin, uint32_t n, int leaf_bytes, unsigned long long* __restrict__ leaves) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = stream + begin + (uint64_t)i * leaf_bytes;
+  unsigned long long v = 0;
+  for (int b = 0; b < leaf_bytes; ++b) v = (v << 8) | __ldg(p + b);
+  leaves[i] = v;
+}
+
+// shared_tree::deserialize, src/shared_tree.cpp:520-538; pointers come back with invariant = false (:162).
+// The stream is copied to the device once; the layers are parsed there (see above), the small top of the
+// tree on the host.  A foreign or damaged stream must not make the device follow wild indices (an illegal
+// address is sticky for the whole process): every non-null child index has to exist in the layer below, the
+// root in the top layer.  The reference trusts its input.
 int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
   static const uint32_t start[4] = {0u, 16u, 4112u, 1052688u};
   t.clear();
+  cudaStream_t st = t.stream;
   uint64_t o = 0;
   auto read_ptr = [&](uint32_t& raw) -> bool {
     if (o >= len) return false;
@@ -278,50 +510,82 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
   if (!read_ptr(root) || !read_u64(n_leaves)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside the header");
   const int leaf_bytes = (t.S + 1) / 2;
   if (n_leaves > (len - o) / (uint64_t)leaf_bytes) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside the leaf table");
-  std::vector<unsigned long long> leaves(n_leaves);
-  for (uint64_t i = 0; i < n_leaves; ++i) {
-    unsigned long long v = 0;
-    for (int b = 0; b < leaf_bytes; ++b) v = (v << 8) | in[o++];
-    leaves[i] = v;
-  }
-  cudaStream_t st = t.stream;
+  if (n_leaves >= IDX_MASK) return t.fail(STB_ERR_BAD_STREAM, "leaf table larger than the pointer format can index");
+
+  // the whole stream on the device (the handle's grow-only staging buffer), zero-padded by one tile
+  const uint64_t padded = ((len + 31) & ~31ull) + DP_TILE + 64;
+  STB_CUDA(t, t.staging.ensure(padded, st));
+  uint8_t* d_stream = reinterpret_cast<uint8_t*>(t.staging.ptr);
+  STB_CUDA(t, cudaMemcpyAsync(d_stream, in, len, cudaMemcpyHostToDevice, st));
+  STB_CUDA(t, cudaMemsetAsync(d_stream + len, 0, padded - len, st));
+
   STB_CUDA(t, t.leaves.alloc(n_leaves, st));
-  STB_CUDA(t, cudaMemcpyAsync(t.leaves.ptr, leaves.data(), n_leaves * 8, cudaMemcpyHostToDevice, st));
-  std::vector<std::vector<uint2>> host_layers;
+  if (n_leaves) {
+    Launch l(t, "parse_leaves");
+    parse_leaves_kernel<<<(unsigned)ceil_div(n_leaves, 256), 256, 0, st>>>(d_stream, o, (uint32_t)n_leaves, leaf_bytes, t.leaves.ptr);
+  }
+  o += n_leaves * (uint64_t)leaf_bytes;
+
+  DevBuf<ParseMap> tile_maps;
+  DevBuf<uint2> tile_entry;
+  DevBuf<unsigned long long> result;
+  STB_CUDA(t, result.alloc(2, st));
+  uint64_t below = n_leaves;
   while (o + 8 <= len) {  // layers until the stream ends (:528-530)
     uint64_t count;
     read_u64(count);
     if (count > (len - o) / 2) return t.fail(STB_ERR_BAD_STREAM, "layer size exceeds the remaining stream");
-    host_layers.emplace_back(count);
-    for (uint64_t i = 0; i < count; ++i) {
-      uint2 nd;
-      if (!read_ptr(nd.x) || !read_ptr(nd.y)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
-      host_layers.back()[i] = nd;
-    }
-  }
-  if (host_layers.empty()) return t.fail(STB_ERR_BAD_STREAM, "stream holds no node layer");
-  // A foreign or damaged stream must not make the device follow wild indices (an illegal address
-  // is sticky for the whole process): every non-null child index has to exist in the layer below,
-  // the root in the top layer.  The reference trusts its input (src/shared_tree.cpp:520-538).
-  {
-    uint64_t below = n_leaves;
-    for (size_t k = 0; k < host_layers.size(); ++k) {
-      for (const uint2& nd : host_layers[k]) {
+    if (count >= IDX_MASK) return t.fail(STB_ERR_BAD_STREAM, "layer larger than the pointer format can index");
+    const size_t k = t.layers.size();
+    t.layers.emplace_back();
+    Layer& layer = t.layers.back();
+    layer.count = count;
+    STB_CUDA(t, layer.nodes.alloc(count, st));
+    if (count <= DP_SMALL) {  // the top of the tree: a few kilobytes, not worth three launches and a read-back
+      std::vector<uint2> nodes(count);
+      for (uint64_t i = 0; i < count; ++i) {
+        uint2 nd;
+        if (!read_ptr(nd.x) || !read_ptr(nd.y)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
         const uint32_t l = nd.x & IDX_MASK, r = nd.y & IDX_MASK;
         if ((l != IDX_MASK && l >= below) || (r != IDX_MASK && r >= below))
           return t.fail(STB_ERR_BAD_STREAM, "a node of layer " + std::to_string(k) + " points past the end of the layer below");
+        nodes[i] = nd;
       }
-      below = host_layers[k].size();
+      STB_CUDA(t, cudaMemcpyAsync(layer.nodes.ptr, nodes.data(), count * sizeof(uint2), cudaMemcpyHostToDevice, st));
+      STB_CUDA(t, cudaStreamSynchronize(st));  // `nodes` is about to go away
+    } else {
+      const uint64_t begin = o & ~31ull;
+      const uint32_t start_off = (uint32_t)(o - begin);
+      const uint64_t extent = std::min<uint64_t>(len - begin, start_off + 8 * count);  // the longest the layer can be
+      const uint32_t tiles = (uint32_t)ceil_div(extent, DP_TILE);
+      STB_CUDA(t, tile_maps.ensure(tiles, st));
+      STB_CUDA(t, tile_entry.ensure(tiles, st));
+      STB_CUDA(t, cudaMemsetAsync(result.ptr, 0, 16, st));
+      {
+        Launch l(t, "parse_tile_maps");
+        parse_tile_maps_kernel<<<tiles, DP_THREADS, 0, st>>>(d_stream, begin, start_off, tile_maps.ptr);
+      }
+      {
+        Launch l(t, "parse_scan_tiles");
+        parse_scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_maps.ptr, tiles, tile_entry.ptr);
+      }
+      {
+        Launch l(t, "parse_emit");
+        parse_emit_kernel<<<tiles, DP_THREADS, 0, st>>>(d_stream, begin, start_off, tile_entry.ptr, reinterpret_cast<uint32_t*>(layer.nodes.ptr),
+                                                        (uint32_t)(2 * count), (uint32_t)below, result.ptr);
+      }
+      unsigned long long res[2] = {0, 0};
+      STB_CUDA(t, cudaMemcpyAsync(res, result.ptr, 16, cudaMemcpyDeviceToHost, st));
+      STB_CUDA(t, cudaStreamSynchronize(st));
+      STB_CUDA(t, cudaGetLastError());
+      if (res[0] == 0 || res[0] > len) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
+      if (res[1]) return t.fail(STB_ERR_BAD_STREAM, "a node of layer " + std::to_string(k) + " points past the end of the layer below");
+      o = res[0];
     }
-    if ((root & IDX_MASK) >= below) return t.fail(STB_ERR_BAD_STREAM, "the root pointer does not index the top layer");
+    below = count;
   }
-  for (auto& hl : host_layers) {
-    t.layers.emplace_back();
-    Layer& layer = t.layers.back();
-    layer.count = hl.size();
-    STB_CUDA(t, layer.nodes.alloc(hl.size(), st));
-    STB_CUDA(t, cudaMemcpyAsync(layer.nodes.ptr, hl.data(), hl.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
-  }
+  if (t.layers.empty()) return t.fail(STB_ERR_BAD_STREAM, "stream holds no node layer");
+  if ((root & IDX_MASK) >= below) return t.fail(STB_ERR_BAD_STREAM, "the root pointer does not index the top layer");
   STB_CUDA(t, cudaStreamSynchronize(st));
   t.n_leaves = n_leaves;
   t.root = root;

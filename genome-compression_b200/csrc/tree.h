@@ -24,7 +24,8 @@ struct Options {
   uint64_t bucket_cap = 3072;            // records a final bucket may hold (<= 3072, what the dedup kernel keeps in registers)
   uint64_t partition_threads = 512;      // CTA size of the partition passes (512 or 1024; 4 records per thread)
   uint64_t dedup_threads = 512;          // CTA size of the bucket dedup kernel (256, 512 or 1024)
-  uint64_t bucket_slack_permille = 125;  // head-room of a first-pass bucket over the mean
+  uint64_t bucket_slack_permille = 125;  // head-room of a first-pass bucket over the mean ...
+  uint64_t bucket_headroom = 1024;       // ... plus this many records (a first-pass bucket that still overflows sends the level to the table in HBM)
   uint64_t child_filter = 1;             // exact singleton filter from the child level's bitmaps (node levels >= 1)
   uint64_t locality = 1;                 // slot proportional to a child id above the first node layer
   uint64_t coop_max = 1ull << 20;        // levels with at most this many pointers run in one cooperative launch

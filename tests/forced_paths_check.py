@@ -2,7 +2,8 @@
 handle's options (stb_set_option), given as name=value arguments:
   bucket_min=1                                  on-chip (bucketed) deduplication of the node levels
   bucket_min=1 bucket_levels=9                  ... of every large-path node level, with the exact singleton filter in front
-  bucket_min=1 bucket_cap=16                    ... with buckets that overflow: the hash-table fallback
+  bucket_min=1 bucket_cap=16                    ... with final buckets that outgrow their regions: the exact-size second pass + chunked dedup
+  bucket_min=1 bucket_slack_permille=0 bucket_headroom=0   ... with first-pass buckets that overflow: the hash-table fallback
   coop_max=0                                    no cooperative middle launch: every level as separate kernels
   stream_chunk_log2=12 stream_min_chunks=2      streaming (chunked) build from host memory"""
 import sys

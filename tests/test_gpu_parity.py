@@ -183,6 +183,47 @@ def test_errors(stb):
     assert e.value.name == "STB_ERR_BAD_STREAM"
 
 
+def test_deserialize_on_device(stb, oracle):
+    """Layers of more than 2048 nodes are parsed on the device (serialize.cu: a 4-state automaton per 32-byte
+    chunk, maps composed by a scan): every pointer length, layer starts at every alignment, damaged streams."""
+    rng = np.random.default_rng(77)
+    for S, n in ((12, 300_000), (3, 200_001), (16, 70_000), (7, 99_999)):
+        # 1-, 2- and 3-byte pointers (4-byte ones need more than 1 052 688 items in a layer: test_large_properties)
+        nib = np.array([1, 2, 4, 8], dtype=np.uint64)[rng.integers(0, 4, size=(n, S))]
+        leaves = (nib << (4 * np.arange(S, dtype=np.uint64))).sum(axis=1).astype(np.uint64)
+        if S == 12:
+            leaves = np.concatenate([leaves, leaves[:50_000], leaves[::-1][:70_000]])
+        want = oracle.build(leaves, S)
+        for sort in (False, True):
+            if sort:
+                want.sort()
+            stream = want.serialize()
+            back = stb.SharedTree(S).deserialize(stream)
+            assert back.layer_counts() == want.layer_counts() and back.leaf_count() == want.leaf_count()
+            assert np.array_equal(back.leaves(), want.leaves())
+            for k in range(back.depth() - 1):
+                got_layer, want_layer = back.layer(k), want.layer(k)
+                # the stream does not keep the invariant bit (src/shared_tree.cpp:162)
+                assert np.array_equal(got_layer, want_layer & np.uint32(0x7fffffff)), (S, sort, k)
+            assert back.serialize() == stream
+            assert np.array_equal(back.decode(), leaves)
+    # damaged streams: cut inside a large layer, and a pointer that indexes past the layer below
+    tree = stb.SharedTree(12).build_from_leaves(leaves[:100_000])
+    stream = tree.serialize()
+    # (a cut inside the last few bytes is not an error by the format: layers are read "until the stream ends",
+    # src/shared_tree.cpp:528-530, so a stream that lost its top layer is a shorter valid stream)
+    for cut in (len(stream) // 2, len(stream) // 3, len(stream) - 40_000):
+        with pytest.raises(stb.StbError) as e:
+            stb.SharedTree(12).deserialize(stream[:cut])
+        assert e.value.name == "STB_ERR_BAD_STREAM", cut
+    head = 1 + 8 + tree.leaf_count() * 6 + 8  # root, leaf count, leaves, layer 0 count (the root of a tree this deep is a 1-byte pointer)
+    bad = bytearray(stream)
+    bad[head + 3000:head + 3004] = bytes([0xCF, 0xFF, 0xFF, 0x00])  # segment 3, offset 0xfffff00: far past the leaf table
+    with pytest.raises(stb.StbError) as e:
+        stb.SharedTree(12).deserialize(bytes(bad))
+    assert e.value.name == "STB_ERR_BAD_STREAM"
+
+
 def test_iupac_and_hash_leaf_path(stb, oracle):
     rng = np.random.default_rng(11)
     codes = np.array([1, 2, 4, 8, 3, 12, 7, 14, 0, 9, 5, 11, 13, 10, 6, 15], dtype=np.uint64)
@@ -342,6 +383,7 @@ def test_large_properties(stb):
     ["bucket_min=1"],
     ["bucket_min=1", "bucket_levels=9", "coop_max=0"],
     ["bucket_min=1", "bucket_cap=16", "bucket_levels=2"],
+    ["bucket_min=1", "bucket_levels=3", "bucket_slack_permille=0", "bucket_headroom=0"],
     ["coop_max=0"],
     ["coop_max=0", "child_filter=0", "locality=0"],
     ["coop_max=65536"],
