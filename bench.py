@@ -782,7 +782,7 @@ def run_b200_dist(args, world, rank, local_rank):
                          "frac": round(ach / peak_gbs, 4), "traffic": None, "peak_source": peak_src,
                          "note": "rank 0's launches of its dominant stage kernel; algorithmic bytes = the record streams of its share of the sharded levels"},
             "cpu_baseline": None, "kernels": kernels,
-            "collectives_per_level": {"barriers": 3, "all_gather_words": world},
+            "sync_per_level": {"nccl_collectives": 0, "peer_exchange_kernels": 4, "what": "barrier + a few counts stored into every peer's arena over NVLink (csrc/shard.cu)"},
             "tree": {"width": n_leaves, "leaves": totals[0], "sharded_layer_nodes": totals[1:]},
         }
         print(json.dumps(line), flush=True)

@@ -37,6 +37,11 @@ constexpr int DD_CAP = 3072;                    // records of a final bucket, he
 constexpr int DD_SLOTS = 4096;                  // shared-memory table: key 8 B + min-position 4 B per slot
 constexpr size_t DD_SMEM = (size_t)DD_SLOTS * 12 + DD_SLOTS / 8;
 
+// overflow[0]: the level cannot be deduplicated on chip (a first-pass bucket outgrew its region, or a final
+// bucket holds more distinct keys than the shared-memory table) - build.cu re-runs it through the table in
+// HBM.  overflow[1]: a final bucket outgrew its fixed region - the exact-size pass takes over.
+__device__ __forceinline__ bool exact_pass_wanted(const uint32_t* overflow) { return overflow[1] != 0u && overflow[0] == 0u; }
+
 __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key) {
   const unsigned long long h = mix64(key);
   return h ^ (h >> 29);
@@ -86,7 +91,8 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
   } else if (PEER) {
     const uint32_t src = by % peer.world, local = by / peer.world;
     const uint32_t bucket = (peer.src << peer.bucket_shift) | local;  // this owner's bucket, in the source's numbering
-    count = min(*reinterpret_cast<const volatile uint32_t*>(peer.base[src] + peer.count_off + 4ull * bucket), in_cap);
+    count = min(peer.counts_in ? __ldg(peer.counts_in + src * peer.counts_stride + local)
+                               : *reinterpret_cast<const volatile uint32_t*>(peer.base[src] + peer.count_off + 4ull * bucket), in_cap);
     if (first >= count) return;
     in_keys = reinterpret_cast<const unsigned long long*>(peer.base[src] + peer.keys_off);
     in_pos = reinterpret_cast<const uint32_t*>(peer.base[src] + peer.pos_off);
@@ -256,10 +262,6 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
                                                          segs, pos_base, peer, nullptr);
 }
 
-// overflow[0]: the level cannot be deduplicated on chip (a first-pass bucket outgrew its region, or a final
-// bucket holds more distinct keys than the shared-memory table) - build.cu re-runs it through the table in
-// HBM.  overflow[1]: a final bucket outgrew its fixed region - the three kernels below take over.
-__device__ __forceinline__ bool exact_pass_wanted(const uint32_t* overflow) { return overflow[1] != 0u && overflow[0] == 0u; }
 
 // exclusive scan of the final buckets' exact record counts; clears the counts (they become the fill state)
 __global__ void __launch_bounds__(1024) exact_offsets_kernel(uint32_t* __restrict__ count2, uint32_t nb, uint32_t* __restrict__ off,
@@ -315,7 +317,9 @@ partition_exact_kernel(const unsigned long long* in_keys, const uint32_t* in_pos
 // answers (a later occurrence and where its key came first; a first occurrence whose key came again)
 // are appended to a list per home rank in THIS rank's memory; the home ranks read their lists after
 // the level's barrier and apply them to their own words (shard.cu: apply_answers_kernel).
-template <int DD_THREADS, bool PEER>
+// EXACT: the buckets lie in exact-size regions (counts = their offsets, one more than there are buckets); the
+// ones that fit the registers are done here, the larger ones by bucket_dedup_chunked_kernel.
+template <int DD_THREADS, bool PEER, bool EXACT = false>
 __global__ void __launch_bounds__(DD_THREADS)
 bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ poss, const uint32_t* __restrict__ counts,
                     uint32_t cap, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits,
@@ -328,11 +332,11 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   __shared__ uint32_t tmin_cnt[STB_MAX_RANKS], tmin_base[STB_MAX_RANKS];  // PEER: answers per home rank
   const uint32_t* overflow_out = overflow;
   if (PEER && threadIdx.x < STB_MAX_RANKS) tmin_cnt[threadIdx.x] = 0u;
-  if (overflow[0] || (!PEER && overflow[1])) return;
+  if (EXACT ? !exact_pass_wanted(overflow) : (overflow[0] || (!PEER && overflow[1]))) return;
   const uint32_t tid = threadIdx.x;
-  const uint32_t count = min(__ldg(counts + blockIdx.x), cap);
-  if (count == 0) return;
-  const uint64_t base = (uint64_t)blockIdx.x * cap;
+  const uint32_t count = EXACT ? __ldg(counts + blockIdx.x + 1) - __ldg(counts + blockIdx.x) : min(__ldg(counts + blockIdx.x), cap);
+  if (count == 0 || (EXACT && count > (uint32_t)DD_CAP)) return;
+  const uint64_t base = EXACT ? (uint64_t)__ldg(counts + blockIdx.x) : (uint64_t)blockIdx.x * cap;
 
   unsigned long long key[DD_ITEMS];
   uint32_t pos[DD_ITEMS];
@@ -438,7 +442,7 @@ bucket_dedup_chunked_kernel(const unsigned long long* __restrict__ keys, const u
   constexpr uint32_t mask = DD_SLOTS - 1;
   for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
     const uint32_t base = __ldg(off + b), count = __ldg(off + b + 1) - base;
-    if (count == 0) continue;
+    if (count <= (uint32_t)DD_CAP) continue;  // done by bucket_dedup_kernel<.., EXACT>
     for (uint32_t i = tid; i < DD_SLOTS; i += DD_THREADS) {
       tkey[i] = EMPTY_KEY;
       tmin[i] = 0xffffffffu;
@@ -543,6 +547,8 @@ static int launch_exact_pass(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl
   const uint32_t tiles_x = (uint32_t)ceil_div(pl.cap1, T * PT_ITEMS), tiles_y = 1u << pl.b1;
   partition_exact_kernel<T><<<(unsigned)std::min<uint64_t>((uint64_t)tiles_x * tiles_y, 148 * (2048 / T)), T, smem, st>>>(
       ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, ws.keys2.ptr, ws.pos2.ptr, count2, 64 - pl.b1 - pl.b2, pl.b2, overflow, exact_off, tiles_x, tiles_y);
+  STB_CUDA(ctx, cudaFuncSetAttribute(bucket_dedup_kernel<D, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  bucket_dedup_kernel<D, false, true><<<nb, D, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, exact_off, 0u, aux, first_bits, multi_bits, overflow, PeerHome{});
   bucket_dedup_chunked_kernel<D><<<std::min<uint32_t>(nb, 148 * 4), D, DD_SMEM, st>>>(ws.keys2.ptr, ws.pos2.ptr, exact_off, nb, aux, first_bits, multi_bits,
                                                                                       overflow);
   return STB_OK;

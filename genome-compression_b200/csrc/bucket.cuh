@@ -28,6 +28,10 @@ struct PeerDest {               // the first-pass buckets of every rank (a sourc
   uint64_t keys_off = 0, pos_off = 0, count_off = 0;  // bucket arrays and their record counts inside an arena
   uint32_t bucket_shift = 0;    // log2(first-pass buckets per owner): bucket d belongs to rank d >> bucket_shift
   uint32_t src = 0, world = 1;  // this rank
+  // the record counts of the segments this rank owns, as every source sent them (local memory:
+  // counts_in[source * counts_stride + local bucket]); null: read them from the sources' arenas
+  const uint32_t* counts_in = nullptr;
+  uint32_t counts_stride = 0;
 };
 
 struct PeerHome {               // where the answers about a position go: a list per home rank, in the owner's arena
@@ -36,6 +40,9 @@ struct PeerHome {               // where the answers about a position go: a list
   uint32_t ans_cap = 0;         // answers one owner can hold for one home rank
   uint32_t self = 0;
   uint32_t log2_positions = 0;  // positions per rank at this level (a power of two): home = position >> log2_positions
+  // how many answers every owner keeps for this rank, as the owners sent them (local: counts_in[owner * counts_stride])
+  const uint32_t* counts_in = nullptr;
+  uint32_t counts_stride = 0;
 };
 
 struct ShardBuckets {

@@ -157,6 +157,9 @@ assign_kernel(uint32_t* __restrict__ tmp, uint32_t n, LevelTable tab, const uint
   __shared__ uint32_t word_pref[33];
   __shared__ uint32_t red[LVL_THREADS / 32];
   const uint32_t rel = blockIdx.x, block = first_block + rel;
+  // a tile without first occurrences has nothing to assign (most tiles of a genome's leaf level: the 4^12
+  // possible leaves have nearly all occurred after the first few per cent of the text)
+  if (rel != gridDim.x - 1 && blockcnt[rel] == 0u) return;
   const uint32_t base = tile_base(rel, blockcnt, chunkcnt, red) + (carry_in ? *carry_in : 0u);
   uint32_t words[LVL_ITERS];
   tile_prefix(bitmask, block, n, words, word_pref);

@@ -1,12 +1,13 @@
 // shard.cu — the sharded multi-GPU build behind ONE C-ABI call per rank (BASELINE.json config 4).
 //
 // The reference builds a tree with one call (tree_constructor::reduce, src/shared_tree.cpp:719-736);
-// so does a rank here: stb_shard_build_from_body.  One process per GPU, NCCL for the plumbing
-// (barriers, one small all-gather per level, the leaf table's all-reduce), peer-mapped memory over
-// NVLink for the data: a level's records go straight from the kernel that makes them into the hash
-// owner's memory, the owner's answers are plain REDs into the home rank's words, and a later
-// occurrence reads the id of its first occurrence from the home rank's pointer array.  Nothing is
-// read by the host inside the level loop.
+// so does a rank here: stb_shard_build_from_body.  One process per GPU, NCCL for the set-up and the
+// leaf level (communicator, exchange of the IPC handles, the leaf table's all-reduce), peer-mapped
+// memory over NVLink for everything inside the level loop: the owners pull a level's records from the
+// ranks that made them, the home ranks pull the owners' answers, a later occurrence reads the id of
+// its first occurrence from the home rank's pointer array, and the four synchronisation points of a
+// level are one tiny kernel each (peer_exchange_kernel: a few numbers and an epoch flag stored into
+// every peer's arena).  Nothing is read by the host inside the level loop.
 //
 // Rank g owns a contiguous, power-of-two aligned range of positions at every sharded level (the
 // analogue of the reference's own 2^22 / 2^25-leaf segments, include/shared_tree.h:305-316), so
@@ -16,14 +17,15 @@
 //
 // Per node level (every per-level cost is O(level / world) on a rank):
 //   partition   local positions -> (key, global position) records, grouped by first-pass bucket in
-//               shared memory, stored into the OWNER's segment for this source (bucket.cu)
-//   barrier
-//   dedup       the owner splits its segments into final buckets and deduplicates each in shared
-//               memory; later occurrences get their first occurrence's position OR-ed into the home
-//               rank's aux word and their first-occurrence bit cleared there
-//   barrier
-//   ids         local counts, one all-gather of the world's totals, local assignment
-//   barrier
+//               shared memory, kept in this rank's arena (bucket.cu)
+//   exchange    barrier + the segments' record counts to their owners
+//   dedup       the owner pulls its segments from every rank, splits them into final buckets and
+//               deduplicates each in shared memory; the answers (a later occurrence and where its key
+//               came first; a first occurrence whose key came again) go into one list per home rank
+//   exchange    barrier + the lists' lengths to the home ranks
+//   apply       the home rank pulls its lists and updates its own words
+//   ids         local counts; exchange: barrier + everybody's count; local assignment
+//   exchange    barrier
 //   resolve     later occurrences fetch the finished pointer of their first occurrence (peer load)
 // Levels of at most `cut` positions are gathered on rank 0 and finished by the single-GPU code.
 #include <dlfcn.h>
@@ -105,6 +107,42 @@ __global__ void min_over_ranks_kernel(uint32_t* __restrict__ out, const uint32_t
   }
 }
 
+// ---- barrier + small all-to-all over peer-mapped memory ----------------------------------------
+// A level of the sharded build needs four synchronisation points, three of which carry a few numbers
+// (record counts per segment, answer counts, unique counts).  As NCCL collectives they cost 75-120 us each
+// on eight GPUs, more than most of the level's kernels; here one warp per peer stores the numbers and
+// then an epoch flag straight into the peer's arena over NVLink, and waits for the peers' flags in its own.
+constexpr uint32_t XCHG_WORDS = 512;  // words one rank can send to one rank per exchange
+constexpr int XCHG_SLOTS = 4;         // mailboxes: an exchange never overwrites what the previous three delivered
+
+struct PeerBox {
+  char* base[STB_MAX_RANKS];
+  uint64_t recv_off, flag_off;
+  uint32_t self, world;
+};
+
+__global__ void __launch_bounds__(STB_MAX_RANKS * 32)
+peer_exchange_kernel(PeerBox box, const uint32_t* __restrict__ send, uint32_t words, uint32_t send_stride, uint32_t epoch, uint32_t* __restrict__ timeout_flag) {
+  const uint32_t peer = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (peer >= box.world) return;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(box.base[peer] + box.recv_off) + (uint64_t)box.self * XCHG_WORDS;
+  for (uint32_t i = lane; i < words; i += 32) dst[i] = send[(uint64_t)peer * send_stride + i];
+  __threadfence_system();  // the numbers before the flag
+  __syncwarp();
+  if (lane == 0) {
+    *reinterpret_cast<volatile uint32_t*>(box.base[peer] + box.flag_off + 4ull * box.self) = epoch;
+    const volatile uint32_t* mine = reinterpret_cast<const volatile uint32_t*>(box.base[box.self] + box.flag_off) + peer;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - epoch) < 0) {
+      if (clock64() - t0 > 8000000000ll) {  // a peer that never arrives (it failed on its own): give up after seconds, not never
+        *timeout_flag = 1u;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
 // ---- the plumbing a rank needs ---------------------------------------------------------------
 struct Comm {
   int rank = 0, world = 1;
@@ -112,6 +150,11 @@ struct Comm {
   virtual int barrier(Ctx& ctx) = 0;                                                  // stream-ordered: later work sees every rank's earlier work
   virtual int all_reduce_min(Ctx& ctx, uint32_t* buf, size_t n) = 0;                  // device, in place
   virtual int all_gather_u32(Ctx& ctx, const uint32_t* send, uint32_t* recv, size_t n) = 0;  // device, n words per rank
+  // All-to-all of a few words + barrier, stream-ordered: `words` words starting at send + r * send_stride go to rank r, which finds
+  // them at its recv + me * XCHG_WORDS; later work on the stream sees every rank's earlier work (words = 0: a plain barrier).
+  // `arena` / `all`: this rank's arena and everybody's (share()); recv_off / flag_off: where the mailbox and the flags lie in an arena.
+  virtual int exchange(Ctx& ctx, char* const* all, uint64_t recv_off, uint64_t flag_off, const uint32_t* send, uint32_t words, uint32_t send_stride,
+                       uint32_t* timeout_flag) = 0;
   virtual int share(Ctx& ctx, char* mine, char** all) = 0;                            // peer-map every rank's arena (cudaMalloc memory)
   virtual void unshare(char** all) = 0;
   virtual int gather_to_root(Ctx& ctx, const void* send, size_t bytes, void* recv, const size_t* bytes_of) = 0;  // device, variable sizes
@@ -137,7 +180,20 @@ struct NcclComm : Comm {
     STB_NCCL(ctx, nccl().AllGather(send, recv, n, ncclUint32, comm, ctx.stream));
     return STB_OK;
   }
+  uint32_t epoch = 0;  // every rank runs the same sequence of exchanges
+  int exchange(Ctx& ctx, char* const* all, uint64_t recv_off, uint64_t flag_off, const uint32_t* send, uint32_t words, uint32_t send_stride,
+               uint32_t* timeout_flag) override {
+    PeerBox box{};
+    for (int r = 0; r < world; ++r) box.base[r] = all[r];
+    box.recv_off = recv_off;
+    box.flag_off = flag_off;
+    box.self = (uint32_t)rank;
+    box.world = (uint32_t)world;
+    peer_exchange_kernel<<<1, STB_MAX_RANKS * 32, 0, ctx.stream>>>(box, send, words, send_stride, ++epoch, timeout_flag);
+    return STB_OK;
+  }
   int share(Ctx& ctx, char* mine, char** all) override {
+    epoch = 0;  // a new arena: its flags are zero
     cudaIpcMemHandle_t h;
     STB_CUDA(ctx, cudaIpcGetMemHandle(&h, mine));
     const size_t hb = sizeof(h);
@@ -235,6 +291,16 @@ struct LocalComm : Comm {
     STB_TRY(sync_all(ctx));
     return STB_OK;
   }
+  int exchange(Ctx& ctx, char* const* all, uint64_t recv_off, uint64_t, const uint32_t* send, uint32_t words, uint32_t send_stride, uint32_t*) override {
+    // threads of one process: everybody's pointers are valid here; the host barrier orders the copies
+    g->slot[rank] = send;
+    STB_TRY(sync_all(ctx));
+    for (int r = 0; r < world && words; ++r)
+      STB_CUDA(ctx, cudaMemcpyAsync(all[rank] + recv_off + (uint64_t)r * XCHG_WORDS * 4, static_cast<const uint32_t*>(g->slot[r]) + (uint64_t)rank * send_stride,
+                                    (size_t)words * 4, cudaMemcpyDeviceToDevice, ctx.stream));
+    STB_TRY(sync_all(ctx));
+    return STB_OK;
+  }
   int share(Ctx& ctx, char* mine, char** all) override {
     g->slot[rank] = mine;
     STB_TRY(sync_all(ctx));
@@ -319,21 +385,35 @@ __global__ void __launch_bounds__(256) leaf_pointers_kernel(uint32_t* __restrict
 }
 
 // The home rank applies the answers about its positions: it reads the list every owner kept for it
-// (coalesced loads over NVLink) and updates its own words.  answer = (position << 32) | first position
-// (a later occurrence) or | 0xffffffff (a first occurrence whose key occurred again).
+// (coalesced loads over NVLink; the lists' lengths arrived with the level's second exchange) and updates
+// its own words.  answer = (position << 32) | first position (a later occurrence) or | 0xffffffff (a first
+// occurrence whose key occurred again).  The lists are walked as one sequence, four loads in flight per thread:
+// a peer's memory answers after a few microseconds.
 __global__ void __launch_bounds__(256)
 apply_answers_kernel(PeerHome home, uint32_t world, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits, uint32_t* __restrict__ multi_bits) {
-  const uint32_t owner = blockIdx.y;
-  const uint32_t count = min(*reinterpret_cast<const volatile uint32_t*>(home.base[owner] + home.ans_count_off + 4ull * home.self), home.ans_cap);
-  const unsigned long long* list = reinterpret_cast<const unsigned long long*>(home.base[owner] + home.ans_off) + (uint64_t)home.self * home.ans_cap;
+  __shared__ uint32_t before[STB_MAX_RANKS + 1];
+  if (threadIdx.x == 0) {
+    uint32_t sum = 0;
+    for (uint32_t o = 0; o < world; ++o) {
+      before[o] = sum;
+      sum += min(__ldg(home.counts_in + o * home.counts_stride), home.ans_cap);
+    }
+    for (uint32_t o = world; o <= STB_MAX_RANKS; ++o) before[o] = sum;
+  }
+  __syncthreads();
+  const uint32_t total = before[world], stride = gridDim.x * 256;
   const uint32_t mask = (1u << home.log2_positions) - 1u;
-  // four loads in flight per thread: the lists of the other ranks answer after a few microseconds
-  for (uint32_t i0 = (blockIdx.x * 256 + threadIdx.x); i0 < count; i0 += gridDim.x * 256 * 4) {
+  for (uint32_t i0 = blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += 4 * stride) {
     unsigned long long a[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t i = i0 + k * gridDim.x * 256;
-      a[k] = i < count ? __ldcs(list + i) : ~0ull;
+      const uint32_t i = i0 + k * stride;
+      a[k] = ~0ull;
+      if (i < total) {
+        uint32_t o = 0;
+        while (before[o + 1] <= i) ++o;
+        a[k] = __ldcs(reinterpret_cast<const unsigned long long*>(home.base[o] + home.ans_off) + (uint64_t)home.self * home.ans_cap + (i - before[o]));
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -347,7 +427,6 @@ apply_answers_kernel(PeerHome home, uint32_t world, uint32_t* __restrict__ aux, 
       }
     }
   }
-  (void)world;
 }
 
 // local number of first occurrences = sum of the chunk totals
@@ -367,11 +446,14 @@ __global__ void __launch_bounds__(256) sum_chunks_kernel(const uint32_t* __restr
 }
 
 // ids of this rank start after the first occurrences of the ranks before it
-__global__ void id_base_kernel(const uint32_t* __restrict__ totals, int rank, int world, uint32_t* __restrict__ base, uint32_t* __restrict__ level_total) {
+__global__ void id_base_kernel(const uint32_t* __restrict__ totals, uint32_t stride, int rank, int world, uint32_t* __restrict__ base,
+                               uint32_t* __restrict__ level_total, uint32_t* __restrict__ keep) {
   uint32_t b = 0, t = 0;
   for (int r = 0; r < world; ++r) {
-    if (r < rank) b += totals[r];
-    t += totals[r];
+    const uint32_t v = totals[(uint64_t)r * stride];
+    keep[r] = v;  // read by the host once, after the build
+    if (r < rank) b += v;
+    t += v;
   }
   *base = b;
   *level_total = t;
@@ -441,6 +523,12 @@ struct Shard : Ctx {
   bool shared = false;
   uint64_t off_ptr[2] = {}, off_aux = 0, off_first[2] = {}, off_multi[2] = {}, off_seg_keys = 0, off_seg_pos = 0, off_seg_count = 0;
   uint64_t off_ans = 0, off_ans_count = 0, ans_records = 0;
+  uint64_t off_box = 0, off_flags = 0;  // mailboxes and epoch flags of Comm::exchange
+  uint64_t box_off(int slot) const { return off_box + (uint64_t)slot * STB_MAX_RANKS * XCHG_WORDS * 4; }
+  const uint32_t* box(int slot) const { return reinterpret_cast<const uint32_t*>(arena + box_off(slot)); }
+  int exchange(int slot, const uint32_t* send, uint32_t words, uint32_t stride) {
+    return comm->exchange(*this, peers, box_off(slot), off_flags, send, words, stride, scalars.ptr + 6);
+  }
 
   // local scratch and results
   DevBuf<uint32_t> dminpos, dids, leaf_bits, tilecnt, count2, scalars, totals_all;
@@ -496,8 +584,11 @@ int ensure_arena(Shard& s) {
   s.ans_records = 2 * P / (uint64_t)s.comm->world + 65536;  // per home rank
   s.off_ans = carve(s.ans_records * 8 * (uint64_t)s.comm->world);
   s.off_ans_count = carve(STB_MAX_RANKS * 4);
+  s.off_box = carve((uint64_t)XCHG_SLOTS * STB_MAX_RANKS * XCHG_WORDS * 4);
+  s.off_flags = carve(STB_MAX_RANKS * 4);
   s.arena_bytes = off;
   STB_CUDA(s, cudaMalloc(&s.arena, s.arena_bytes));
+  STB_CUDA(s, cudaMemsetAsync(s.arena + s.off_flags, 0, STB_MAX_RANKS * 4, s.stream));  // before anybody can see the arena
   s.arena_shard = s.shard;
   STB_TRY(s.comm->share(s, s.arena, s.peers));
   s.shared = true;
@@ -529,6 +620,10 @@ ShardBuckets level_buckets(const Shard& s, uint64_t n_total, uint64_t P, int lev
   sb.home.self = (uint32_t)s.comm->rank;
   sb.home.log2_positions = (uint32_t)log2_exact(P);
   for (int r = 0; r < s.comm->world; ++r) sb.dest.base[r] = sb.home.base[r] = s.peers[r];
+  sb.dest.counts_in = s.box(0);
+  sb.dest.counts_stride = XCHG_WORDS;
+  sb.home.counts_in = s.box(1);
+  sb.home.counts_stride = XCHG_WORDS;
   (void)level_parity;
   (void)out_ptr;
   return sb;
@@ -562,7 +657,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     const uint64_t tiles = ceil_div(n0, LVL_TILE);
     STB_CUDA(s, s.tilecnt.ensure(tiles + tiles / CHUNK_TILES + 2, st));
   }
-  STB_CUDA(s, s.scalars.ensure(8, st));  // [0] local total, [1] id base, [2] level total, [3] overflow
+  STB_CUDA(s, s.scalars.ensure(8, st));  // [0] local total, [1] id base, [2] level total, [3] overflow, [4] leaf flag, [5] assign's total, [6] barrier timeout
   STB_CUDA(s, s.totals_all.ensure((uint64_t)world * 48 + 48, st));
   STB_CUDA(s, s.leaves.ensure(std::min<uint64_t>(n0, canon_entries) + 1, st));
   STB_CUDA(s, cudaMemsetAsync(s.scalars.ptr, 0, 8 * 4, st));
@@ -641,14 +736,14 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     STB_TRY(shard_partition(s, sb, ptr_cur, (uint32_t)n_cur_local, (uint32_t)n_next_local, (uint32_t)lo, child_first, child_multi, aux, first_bits,
                             multi_bits, seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
     {
-      Launch l(s, "collective_barrier", false);
-      STB_TRY(comm.barrier(s));  // every rank's buckets are complete: the owners pull them
+      Launch l(s, "peer_exchange");
+      STB_TRY(s.exchange(0, seg_count, local1, local1));  // every rank's buckets are complete and the owners know their sizes: they pull them
     }
     STB_CUDA(s, s.count2.ensure((uint64_t)local1 << sb.b2, st));
     STB_TRY(shard_dedup(s, sb, s.ws, s.count2.ptr, s.scalars.ptr + 3));
     {
-      Launch l(s, "collective_barrier", false);
-      STB_TRY(comm.barrier(s));  // every owner's answer lists are complete: the home ranks pull them
+      Launch l(s, "peer_exchange");
+      STB_TRY(s.exchange(1, reinterpret_cast<const uint32_t*>(s.arena + s.off_ans_count), 1, 1));  // the answer lists are complete, their lengths delivered
     }
     if (s.opt.profile_levels > 1) {  // debugging aid: how many answers this owner keeps for every home rank
       uint32_t kept[STB_MAX_RANKS];
@@ -660,7 +755,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     }
     {
       Launch l(s, "shard_apply");
-      apply_answers_kernel<<<dim3(1184, world), 256, 0, st>>>(sb.home, (uint32_t)world, aux, first_bits, multi_bits);
+      apply_answers_kernel<<<1184, 256, 0, st>>>(sb.home, (uint32_t)world, aux, first_bits, multi_bits);
     }
     // ids: local counts -> the world's totals -> this rank's base
     const uint32_t tiles = (uint32_t)ceil_div(n_next_local, LVL_TILE), chunks = tiles / CHUNK_TILES + 1;
@@ -673,10 +768,10 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     sum_chunks_kernel<<<1, 256, 0, st>>>(chunkcnt, chunks, s.scalars.ptr);
     uint32_t* totals = s.totals_all.ptr + (uint64_t)(j + 1) * world;
     {
-      Launch l(s, "collective_totals", false);
-      STB_TRY(comm.all_gather_u32(s, s.scalars.ptr, totals, 1));
+      Launch l(s, "peer_exchange");
+      STB_TRY(s.exchange(2, s.scalars.ptr, 1, 0));  // everybody's number of first occurrences
     }
-    id_base_kernel<<<1, 1, 0, st>>>(totals, rank, world, s.scalars.ptr + 1, s.scalars.ptr + 2);
+    id_base_kernel<<<1, 1, 0, st>>>(s.box(2), XCHG_WORDS, rank, world, s.scalars.ptr + 1, s.scalars.ptr + 2, totals);
     s.slices.emplace_back();
     STB_CUDA(s, s.slices.back().alloc(std::max<uint64_t>(n_next_local, 1), st));
     if (tiles) {
@@ -686,8 +781,8 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
                                                               s.scalars.ptr + 5, s.slices.back().ptr, S, ptr_cur, (uint32_t)n_cur_local, s.scalars.ptr + 1);
     }
     {
-      Launch l(s, "collective_barrier", false);
-      STB_TRY(comm.barrier(s));  // every rank's first occurrences have their ids
+      Launch l(s, "peer_exchange");
+      STB_TRY(s.exchange(3, nullptr, 0, 0));  // every rank's first occurrences have their ids
     }
     if (tiles) {
       Launch l(s, "shard_resolve");
@@ -700,7 +795,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
 
   // ---- the top of the tree on rank 0 ----
   s.profile_level = s.opt.profile_levels ? L : -1;
-  STB_TRY(comm.barrier(s));  // every rank's last pointer array is final
+  STB_TRY(s.exchange(0, nullptr, 0, 0));  // every rank's last pointer array is final
   const uint64_t n_top = s.level_total(L - 1);
   if (rank == 0) {
     Launch l(s, "root_top_levels", false);
@@ -718,7 +813,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     const int rc = build_upper_levels(up, top.ptr, n_top, L == 1);
     if (rc != STB_OK) return s.fail(rc, up.error);
   }
-  STB_TRY(comm.barrier(s));  // rank 0 has read the peers' arrays: the arenas may be reused
+  STB_TRY(s.exchange(1, nullptr, 0, 0));  // rank 0 has read the peers' arrays: the arenas may be reused
 
   s.profile_level = -1;
   // ---- what the host needs to know, once ----
@@ -728,8 +823,11 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   STB_TRY(comm.all_gather_u32(s, s.scalars.ptr + 3, gathered_flags, 1));
   STB_CUDA(s, cudaMemcpyAsync(s.h_totals.data(), s.totals_all.ptr, s.h_totals.size() * 4, cudaMemcpyDeviceToHost, st));
   STB_CUDA(s, cudaMemcpyAsync(overflowed.data(), gathered_flags, world * 4, cudaMemcpyDeviceToHost, st));
+  uint32_t timed_out = 0;
+  STB_CUDA(s, cudaMemcpyAsync(&timed_out, s.scalars.ptr + 6, 4, cudaMemcpyDeviceToHost, st));
   STB_CUDA(s, cudaStreamSynchronize(st));
   STB_CUDA(s, cudaGetLastError());
+  if (timed_out) return s.fail(STB_ERR_CUDA, "sharded build: a rank did not reach a level's barrier within seconds (did it fail on its own?)");
   s.whole_on_root = false;
   for (uint32_t f : overflowed)
     if (f) s.whole_on_root = true;
