@@ -388,11 +388,17 @@ parse_scan_tiles_kernel(const ParseMap* __restrict__ tile_maps, uint32_t tiles, 
     }
     if (lane == 31) warp_maps[warp] = incl;
     __syncthreads();
-    ParseMap before = identity_map(), total = identity_map();
-    for (uint32_t w = 0; w < 32; ++w) {
-      if (w == warp) before = total;
-      total = compose(total, warp_maps[w]);
+    if (warp == 0) {  // inclusive scan of the 32 warp totals
+      ParseMap w = warp_maps[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const ParseMap up = shfl_up_map(w, d);
+        if (lane >= (uint32_t)d) w = compose(up, w);
+      }
+      warp_maps[lane] = w;
     }
+    __syncthreads();
+    const ParseMap before = warp ? warp_maps[warp - 1] : identity_map(), total = warp_maps[31];
     ParseMap excl = shfl_up_map(incl, 1);
     if (lane == 0) excl = identity_map();
     excl = compose(before, excl);

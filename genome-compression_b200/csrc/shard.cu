@@ -509,8 +509,9 @@ struct Shard : Ctx {
     const uint64_t per = std::max<uint64_t>(1, ceil_div(n, world));
     shard = 1;
     while (shard < per) shard <<= 1;
-    // below this many positions a level costs less on one GPU than its three barriers cost the world
-    cut = opt_cut ? opt_cut : std::max<uint64_t>(1ull << 20, (1ull << 25) / world);
+    // below this many positions a level costs less on rank 0 alone than its four exchanges and the pulls over
+    // NVLink cost the world (measured at 3.1 Gbp: 8 M / 4 M / 2-4 M positions at 2 / 4 / 8 ranks, profiles/README.md)
+    cut = opt_cut ? opt_cut : std::max<uint64_t>(1ull << 20, (1ull << 24) / world);
     pointer_levels = 1;
     while ((shard >> pointer_levels) >= 1 && level_total(pointer_levels) > cut && level_total(pointer_levels) > 1) ++pointer_levels;
   }
