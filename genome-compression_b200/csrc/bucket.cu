@@ -13,8 +13,9 @@
 //                 bucket holds ~2 K records                               [HBM stream]
 //   dedup         one CTA per final bucket: records -> shared memory, open-addressing table in
 //                 shared memory, min-position per key.  A record that is not its key's minimum
-//                 is a later occurrence: its first-occurrence bit is cleared and the position of
-//                 the first occurrence is OR-ed into aux[position]; a first occurrence whose key
+//                 is a later occurrence: its first-occurrence bit is cleared and aux[position] =
+//                 its flags (they travel in the record's position word) | the position of the first
+//                 occurrence; a first occurrence whose key
 //                 occurs again is marked in the level's `multi` bitmap (the exact singleton
 //                 filter of the level above reads it).                    [HBM stream + sparse REDs]
 //
@@ -62,7 +63,13 @@ __device__ __forceinline__ unsigned long long bucket_hash(unsigned long long key
 // occurrences, e.g. the node of two all-N leaves once per N run): the first attempt has counted every final
 // bucket exactly (the counter is bumped before the capacity check), so the records are scattered again into
 // regions of exactly those sizes (exact_off = exclusive scan of the counts, exact_cursor = fill state).
-template <bool FROM_CHILDREN, int PT_THREADS, bool PEER, bool EXACT>
+__device__ __forceinline__ uint32_t finish_leaf(uint32_t t, const LeafFinish& leaf) {
+  const uint32_t s = t & IDX_MASK;
+  const uint32_t id = (s & LEAF_SIDE) ? (__ldcg(leaf.words + __ldcg(&leaf.side[s & (LEAF_SIDE - 1u)].minpos)) & IDX_MASK) : __ldcg(leaf.dids + s);
+  return finish_pointer(id, t & ~IDX_MASK);
+}
+
+template <bool FROM_CHILDREN, int PT_THREADS, bool PEER, bool EXACT, bool LEAF = false>
 __device__ __forceinline__ void
 partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_next,
                const unsigned long long* in_keys, const uint32_t* in_pos,
@@ -70,7 +77,8 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
                unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos, uint32_t* __restrict__ out_count,
                uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
                uint32_t* __restrict__ multi_bits, const uint32_t* __restrict__ child_first, const uint32_t* __restrict__ child_multi,
-               uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, const PeerDest& peer, const uint32_t* __restrict__ exact_off) {
+               uint32_t* __restrict__ overflow, uint32_t segs, uint32_t pos_base, const PeerDest& peer, const uint32_t* __restrict__ exact_off,
+               const LeafFinish& leaf = LeafFinish{}) {
   constexpr int PT_TILE = PT_THREADS * PT_ITEMS, PT_WARPS = PT_THREADS / 32;
   extern __shared__ __align__(16) uint8_t smem[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(smem);
@@ -103,6 +111,32 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
     in_base = (uint64_t)by * in_cap;
   }
   for (uint32_t i = tid; i < nb; i += PT_THREADS) hist[i] = 0;
+  uint2* schild = reinterpret_cast<uint2*>(smem);  // LEAF: the tile's finished children (the staging area is not in use yet)
+  if (FROM_CHILDREN && LEAF) {
+    // the children are leaf words: finish the later occurrences (id from the table), write them back, and keep
+    // the tile's pairs in shared memory for the neighbour comparison below
+#pragma unroll
+    for (int it = 0; it < PT_ITEMS; ++it) {
+      const uint32_t o = it * PT_THREADS + tid, i = first + o;
+      if (i < count) {
+        const bool pair = 2 * (uint64_t)i + 1 < n_cur;
+        uint32_t l, r = PTR_NULL;
+        if (pair) {
+          const uint2 pr = __ldcg(reinterpret_cast<const uint2*>(leaf.words) + i);
+          l = pr.x;
+          r = pr.y;
+        } else {
+          l = __ldcg(leaf.words + 2 * (uint64_t)i);
+        }
+        const uint32_t firsts = __ldg(leaf.first_bits + (i >> 4)) >> ((2u * i) & 31u);
+        if (!(firsts & 1u)) l = finish_leaf(l, leaf);
+        if (pair && !(firsts & 2u)) r = finish_leaf(r, leaf);
+        if (pair) reinterpret_cast<uint2*>(leaf.words)[i] = make_uint2(l, r);
+        else leaf.words[2 * (uint64_t)i] = l;
+        schild[o] = make_uint2(l, r);
+      }
+    }
+  }
   __syncthreads();
 
   unsigned long long key[PT_ITEMS];
@@ -131,7 +165,16 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
       pos[it] = pos_base + i;
       uint32_t l = 0, r = 0;
       bool same = false;  // the same children as the position before it (runs of N, of one letter, of a short period)
-      if (valid) {
+      if (valid && LEAF) {
+        const uint32_t o = it * PT_THREADS + tid;
+        const uint2 pr = schild[o];
+        l = pr.x;
+        r = pr.y;
+        if (o > 0) {
+          const uint2 before = schild[o - 1];
+          same = before.x == l && before.y == r;
+        }
+      } else if (valid) {
         if (2 * (uint64_t)i + 1 < n_cur) {
           const uint2 pr = __ldg(reinterpret_cast<const uint2*>(cur) + i);
           l = pr.x;
@@ -166,7 +209,9 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
       if (valid || collapsed[it]) {
         canonical_node(l, r, cl, cr, f);
         key[it] = pair_key(cl, cr);
-        if (valid) aux[i] = f;  // flags at bits 29..31; the dedup kernel ORs the first occurrence's position below them
+        // the flags (bits 29..31) travel in the record's position word: only a later occurrence needs them again
+        // (the dedup kernel writes aux[position] = flags | first position; a first occurrence is recomputed by assign)
+        if (valid) pos[it] |= f;
       }
       flag_of[it] = f;
     }
@@ -260,6 +305,17 @@ partition_kernel(const uint32_t* __restrict__ cur, uint32_t n_cur, uint32_t n_ne
   partition_tile<FROM_CHILDREN, PT_THREADS, PEER, false>(blockIdx.x, blockIdx.y, cur, n_cur, n_next, in_keys, in_pos, in_count, in_cap, out_keys, out_pos,
                                                          out_count, out_cap, shift, bits, aux, first_bits, multi_bits, child_first, child_multi, overflow,
                                                          segs, pos_base, peer, nullptr);
+}
+
+// the first node level over leaf words that are finished on the way (LeafFinish)
+template <int PT_THREADS>
+__global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
+partition_leaves_kernel(LeafFinish leaf, uint32_t n_cur, uint32_t n_next, unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos,
+                        uint32_t* __restrict__ out_count, uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
+                        uint32_t* __restrict__ multi_bits, uint32_t* __restrict__ overflow) {
+  partition_tile<true, PT_THREADS, false, false, true>(blockIdx.x, 0u, nullptr, n_cur, n_next, nullptr, nullptr, nullptr, 0u, out_keys, out_pos, out_count,
+                                                       out_cap, shift, bits, aux, first_bits, multi_bits, nullptr, nullptr, overflow, 1u, 0u, PeerDest{},
+                                                       nullptr, leaf);
 }
 
 
@@ -376,7 +432,7 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
       }
       h = (h + 1) & mask;
     }
-    atomicMin(&tmin[h], pos[j]);
+    atomicMin(&tmin[h], pos[j] & IDX_MASK);
     slot[j] = h;
   }
   __syncthreads();
@@ -384,17 +440,17 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
   for (int j = 0; j < DD_ITEMS; ++j) {
     const uint32_t i = j * DD_THREADS + tid;
     if (i >= count) continue;
-    const uint32_t p = pos[j], h = slot[j], fp = tmin[h];
+    const uint32_t p = pos[j] & IDX_MASK, h = slot[j], fp = tmin[h];
     const bool later = fp != p;
     const bool again = !later && ((tmulti[h >> 5] >> (h & 31)) & 1u);
     if (PEER) {
-      // answer = (position << 32) | first position, or | 0xffffffff for "this first occurrence occurs again";
+      // answer = (flags | position) << 32 | first position, or | 0xffffffff for "this first occurrence occurs again";
       // kept in registers until the CTA has reserved room in the lists
       slot[j] = later ? fp : (again ? 0xffffffffu : 0xfffffffeu);
       if (later || again) atomicAdd(&tmin_cnt[p >> home.log2_positions], 1u);
     } else if (later) {  // a later occurrence: not a first, and it points at the first
       atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
-      atomicOr(aux + p, fp);
+      aux[p] = (pos[j] & ~IDX_MASK) | fp;
     } else if (again) {
       atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
     }
@@ -416,7 +472,7 @@ bucket_dedup_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
     for (int j = 0; j < DD_ITEMS; ++j) {
       const uint32_t i = j * DD_THREADS + tid;
       if (i >= count || slot[j] == 0xfffffffeu) continue;
-      const uint32_t hr = pos[j] >> home.log2_positions;
+      const uint32_t hr = (pos[j] & IDX_MASK) >> home.log2_positions;
       const uint32_t at = tmin_base[hr] + atomicAdd(&tmin_cnt[hr], 1u);
       if (at < home.ans_cap)
         reinterpret_cast<unsigned long long*>(home.base[home.self] + home.ans_off)[(uint64_t)hr * home.ans_cap + at] =
@@ -466,7 +522,7 @@ bucket_dedup_chunked_kernel(const unsigned long long* __restrict__ keys, const u
         if (++steps == DD_SLOTS) break;  // every slot holds another key
       }
       if (steps == DD_SLOTS) full = 1u;
-      else if (tmin[h] > pos) atomicMin(&tmin[h], pos);
+      else if (tmin[h] > (pos & IDX_MASK)) atomicMin(&tmin[h], pos & IDX_MASK);
     }
     __syncthreads();
     if (full) {
@@ -475,13 +531,13 @@ bucket_dedup_chunked_kernel(const unsigned long long* __restrict__ keys, const u
     }
     for (uint32_t i = tid; i < count; i += DD_THREADS) {
       const unsigned long long key = __ldg(keys + base + i);
-      const uint32_t p = __ldg(poss + base + i);
+      const uint32_t pf = __ldg(poss + base + i), p = pf & IDX_MASK;
       uint32_t h = (uint32_t)bucket_hash(key) & mask;
       while (tkey[h] != key) h = (h + 1) & mask;
       const uint32_t fp = tmin[h];
       if (fp != p) {  // a later occurrence: not a first, and it points at the first
         atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
-        atomicOr(aux + p, fp);
+        aux[p] = (pf & ~IDX_MASK) | fp;
       } else if ((tmulti[h >> 5] >> (h & 31)) & 1u) {
         atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
       }
@@ -512,13 +568,18 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt) {
 template <int T>
 static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
                              const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
-                             uint32_t* count1, uint32_t* count2, uint32_t* overflow) {
+                             uint32_t* count1, uint32_t* count2, uint32_t* overflow, const LeafFinish* leaf) {
   cudaStream_t st = ctx.stream;
   constexpr int TILE = T * PT_ITEMS;
   const size_t smem = pt_smem(T);
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_leaves_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<false, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
+  if (leaf) {
+    Launch l(ctx, "bucket_partition");
+    partition_leaves_kernel<T><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(*leaf, n_cur, n_next, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1,
+                                                                               pl.b1, aux, first_bits, multi_bits, overflow);
+  } else {
     Launch l(ctx, "bucket_partition");
     partition_kernel<true, T, false><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(
         cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1, pl.b1, aux, first_bits, multi_bits,
@@ -620,7 +681,7 @@ int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl) {
 
 int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
                        const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
-                       uint32_t** overflow_out) {
+                       uint32_t** overflow_out, const LeafFinish* leaf) {
   cudaStream_t st = ctx.stream;
   STB_TRY(bucket_reserve(ctx, ws, pl));
   const uint32_t nb1 = 1u << pl.b1, nb = 1u << (pl.b1 + pl.b2);
@@ -630,9 +691,9 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl, cons
   uint32_t* exact_off = overflow + 2;
   STB_CUDA(ctx, cudaMemsetAsync(ws.counters.ptr, 0, ((uint64_t)nb1 + nb + 2) * 4, st));
   if (pl.partition_threads == 512)
-    STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow));
+    STB_TRY(launch_partitions<512>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow, leaf));
   else
-    STB_TRY(launch_partitions<1024>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow));
+    STB_TRY(launch_partitions<1024>(ctx, ws, pl, cur, n_cur, n_next, child_first, child_multi, aux, first_bits, multi_bits, count1, count2, overflow, leaf));
   if (pl.dedup_threads == 256) STB_TRY(launch_dedup<256>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else if (pl.dedup_threads == 512) STB_TRY(launch_dedup<512>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));
   else STB_TRY(launch_dedup<1024>(ctx, ws, pl, nb, count2, aux, first_bits, multi_bits, overflow));

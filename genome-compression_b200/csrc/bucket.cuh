@@ -53,6 +53,19 @@ struct ShardBuckets {
   PeerHome home;
 };
 
+// Leaf pointers finished on the fly by the first node level's partition pass (ACGT text through the direct
+// leaf table).  That pass is the first kernel to hold both children of a node position, and the 258 M lookups in
+// the L2-resident id table hide behind its integer work instead of being a kernel of their own (resolve<leaf>,
+// 1.2 ms at 3.1 Gbp).  The pass writes the finished pointers back, so every later reader sees what resolve<leaf>
+// would have left.
+struct LeafFinish {
+  uint32_t* words = nullptr;             // the leaf level's per-position words: finished pointers at the first occurrences,
+                                         // canonical code | flags (or LEAF_SIDE | side slot | flags) everywhere else
+  const uint32_t* first_bits = nullptr;  // the leaf level's first occurrences
+  const uint32_t* dids = nullptr;        // id by canonical 2-bit code
+  const Slot* side = nullptr;            // leaves outside ACGT: min-position per leaf (its word holds the id)
+};
+
 struct BucketWorkspace {
   DevBuf<unsigned long long> keys1, keys2;
   DevBuf<uint32_t> pos1, pos2, counters;
@@ -62,14 +75,15 @@ BucketPlan bucket_plan(uint64_t n, const Options& opt);
 int bucket_reserve(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan);
 
 // Deduplicates the node level whose children are cur[0, n_cur): afterwards first_bits marks the
-// first occurrences, aux[p] = flags(p) | position of p's first occurrence (later occurrences) or
-// flags(p) alone (first occurrences), multi_bits marks the first occurrences whose key occurs
+// first occurrences, aux[p] = flags(p) | position of p's first occurrence for the later occurrences
+// (aux is not written for first occurrences: assign recomputes them), multi_bits marks the first occurrences whose key occurs
 // again.  child_first / child_multi (optional): the child level's bitmaps; a position with a child
 // that never repeats is a certified singleton and makes no record (build.cu: children_both_repeat).
 // first_bits (tile-rounded) and multi_bits must be zero on entry.  *overflow_out is a
 // device flag: non-zero means a bucket overflowed and nothing of the above was produced.
 int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan, const uint32_t* cur, uint32_t n_cur, uint32_t n_next,
-                       const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out);
+                       const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits, uint32_t** overflow_out,
+                       const LeafFinish* leaf = nullptr);
 
 // shard.cu drives these: see ShardBuckets.  seg_*: this rank's first-pass buckets (2^b1 x cap_seg records and
 // their counts, in its arena); the owner's split reads every rank's through `dest`.

@@ -595,7 +595,7 @@ void launch_leaf_text(Ctx& ctx, const char* body, uint64_t n, LevelTable tab, ui
 template <int MODE>
 int finish_level(Ctx& ctx, const uint32_t* aux, uint32_t* out, uint32_t n, LevelTable tab, const uint32_t* bitmask, uint32_t* tilecnt,
                  uint32_t* total_out, void* uniq, const uint32_t* children = nullptr, uint32_t n_children = 0, uint32_t* multi_bits = nullptr,
-                 const uint32_t* firstpos_unless = nullptr) {
+                 const uint32_t* firstpos_unless = nullptr, bool skip_resolve = false) {
   const unsigned nb = (unsigned)ceil_div(n, LVL_TILE);
   uint32_t* chunkcnt = tilecnt + nb;
   STB_CUDA(ctx, cudaMemsetAsync(chunkcnt, 0, (nb / CHUNK_TILES + 1) * 4, ctx.stream));
@@ -608,7 +608,7 @@ int finish_level(Ctx& ctx, const uint32_t* aux, uint32_t* out, uint32_t n, Level
     assign_kernel<MODE><<<nb, LVL_THREADS, 0, ctx.stream>>>(out, n, tab, bitmask, tilecnt, chunkcnt, 0u, nullptr, total_out, uniq, ctx.S, children,
                                                             n_children);
   }
-  {
+  if (!skip_resolve) {
     Launch l(ctx, "resolve_ids");
     if (MODE == MODE_LEAF_DIRECT) resolve_kernel<RESOLVE_DIRECT><<<nb, LVL_THREADS, 0, ctx.stream>>>(aux, out, n, tab, bitmask, 0u, nullptr, nullptr);
     else resolve_kernel<RESOLVE_TABLE><<<nb, LVL_THREADS, 0, ctx.stream>>>(aux, out, n, tab, bitmask, 0u, multi_bits, firstpos_unless);
@@ -645,11 +645,18 @@ int reserve_node_workspace(Tree& t, Scratch& sc, uint64_t n_cur) {
   return STB_OK;
 }
 
+// The on-chip (bucketed) plan of node level `level` with n_next positions, or an unusable one.
+BucketPlan level_bucket_plan(const Tree& t, uint64_t n_next, int level) {
+  return (n_next >= t.opt.bucket_min && (uint64_t)level < t.opt.bucket_levels) ? bucket_plan(n_next, t.opt) : BucketPlan{};
+}
+
 // Node levels from a pointer array down to a single root pointer.  Appends one layer per
 // level to t.layers; counts_dev[level] receives each layer's size; returns the buffer that
 // holds the root pointer in *root_buf.  The workspace must have been reserved for n_cur.
+// `leaf` (optional): `cur` holds leaf words whose later occurrences are still unresolved; the first level is then
+// bucketed (the caller checked level_bucket_plan) and its partition pass finishes them (LeafFinish).
 int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t n_cur, uint32_t* counts_dev, int* levels_out,
-                    uint32_t** root_buf) {
+                    uint32_t** root_buf, const LeafFinish* leaf = nullptr) {
   cudaStream_t st = t.stream;
   int level = 0;
   if (!sc.tags_cleared) {
@@ -681,7 +688,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     }
     const uint32_t par = (uint32_t)level & 1u;
     const uint64_t n_next = ceil_div(n_cur, 2);
-    const BucketPlan pl = (n_next >= t.opt.bucket_min && (uint64_t)level < t.opt.bucket_levels) ? bucket_plan(n_next, t.opt) : BucketPlan{};
+    const BucketPlan pl = level_bucket_plan(t, n_next, level);
     if (!pl.usable && n_cur <= t.opt.coop_max) {  // the middle of the tree in one cooperative launch
       if (sc.coop_grid == 0) {
         int per_sm = 0, sms = 0;
@@ -739,7 +746,7 @@ int run_node_levels(Tree& t, Scratch& sc, uint32_t* cur, uint32_t* nxt, uint64_t
     if (pl.usable) {
       // on chip (bucket.cu); the hash-table kernels below then run only if a bucket overflowed
       STB_TRY(bucket_dedup_level(t, sc.bucket, pl, cur, (uint32_t)n_cur, (uint32_t)n_next, child_first, child_multi, sc.aux.ptr, first_bits, multi_bits,
-                                 &overflow));
+                                 &overflow, level == 0 ? leaf : nullptr));
       Launch l(t, "bucket_fallback");
       bitmaps_reset_kernel<<<296, 256, 0, st>>>(first_bits, multi_bits, (uint32_t)bitmap_words(n_next), overflow);
     }
@@ -879,14 +886,20 @@ int build_impl(Tree& t, const LeafInput& in, uint64_t n0, bool direct) {
     if (direct) leaf_insert_u64_kernel<true><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
     else leaf_insert_u64_kernel<false><<<nb, LVL_THREADS, 0, st>>>(in.leaves, (uint32_t)n0, S, tab, sc.ptr_a.ptr, sc.flags.ptr);
   }
-  if (direct) STB_TRY(finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.tilecnt.ptr, sc.counts.ptr, t.leaves.ptr));
+  // direct leaf level under a bucketed first node level: the later occurrences are resolved by that level's
+  // partition pass (LeafFinish), not by a kernel of their own
+  LeafFinish leaf_finish{sc.ptr_a.ptr, sc.bitmask.ptr, sc.dids.ptr, sc.side_slots.ptr};
+  const bool fuse_leaf = direct && n0 > SMALL_MAX && level_bucket_plan(t, ceil_div(n0, 2), 0).usable;
+  if (direct)
+    STB_TRY(finish_level<MODE_LEAF_DIRECT>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.tilecnt.ptr, sc.counts.ptr, t.leaves.ptr, nullptr,
+                                           0, nullptr, nullptr, fuse_leaf));
   else STB_TRY(finish_level<MODE_LEAF_HASH>(t, sc.ptr_a.ptr, sc.ptr_a.ptr, (uint32_t)n0, tab, sc.bitmask.ptr, sc.tilecnt.ptr, sc.counts.ptr, t.leaves.ptr));
 
   // ---- node levels ----
   t.layers.clear();
   int level = 0;
   uint32_t* cur = nullptr;
-  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n0, sc.counts.ptr + 1, &level, &cur));
+  STB_TRY(run_node_levels(t, sc, sc.ptr_a.ptr, sc.ptr_b.ptr, n0, sc.counts.ptr + 1, &level, &cur, fuse_leaf ? &leaf_finish : nullptr));
   // `cur` now holds the single root pointer.
   t.profile_level = -1;
 

@@ -27,6 +27,10 @@ constexpr uint32_t KEY31 = 0x7fffffffu;
 constexpr uint32_t PTR_NULL = 0x9fffffffu;
 constexpr unsigned long long EMPTY_KEY = 0xffffffffffffffffull;
 
+// direct leaf mode: a per-position word with this bit names a slot of the side table (a leaf with
+// symbols outside ACGT) instead of a 2-bit code of the direct table (codes are below 2^24)
+constexpr uint32_t LEAF_SIDE = 1u << 28;
+
 // pointer{index, m, t, inv} (reference src/shared_tree.cpp:86-87).  `flags` carries
 // m/t/inv already at bits 29/30/31; the mirror bit is dropped on invariant targets.
 __host__ __device__ __forceinline__ uint32_t finish_pointer(uint32_t index, uint32_t flags) {

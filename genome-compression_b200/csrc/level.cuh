@@ -31,10 +31,6 @@ __device__ __forceinline__ void load_children(const uint32_t* __restrict__ cur, 
 
 enum { MODE_LEAF_DIRECT = 0, MODE_LEAF_HASH = 1, MODE_NODE = 2 };
 
-// direct leaf mode: a per-position word with this bit names a slot of the side table (a leaf with
-// symbols outside ACGT) instead of a 2-bit code of the direct table (codes are below 2^24)
-constexpr uint32_t LEAF_SIDE = 1u << 28;
-
 // Loads the tile's 32 bitmap words (one per warp and iteration), leaves the exclusive prefix of
 // their popcounts in word_pref[0..31] and the tile's total in word_pref[32].
 __device__ __forceinline__ void tile_prefix(const uint32_t* __restrict__ bitmask, uint32_t block, uint32_t n, uint32_t (&words)[LVL_ITERS],

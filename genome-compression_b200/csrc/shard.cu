@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) leaf_pointers_kernel(uint32_t* __restrict
 
 // The home rank applies the answers about its positions: it reads the list every owner kept for it
 // (coalesced loads over NVLink; the lists' lengths arrived with the level's second exchange) and updates
-// its own words.  answer = (position << 32) | first position (a later occurrence) or | 0xffffffff (a first
+// its own words.  answer = (flags | position) << 32 | first position (a later occurrence) or | 0xffffffff (a first
 // occurrence whose key occurred again).  The lists are walked as one sequence, four loads in flight per thread:
 // a peer's memory answers after a few microseconds.
 __global__ void __launch_bounds__(256)
@@ -418,12 +418,12 @@ apply_answers_kernel(PeerHome home, uint32_t world, uint32_t* __restrict__ aux, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (a[k] == ~0ull) continue;
-      const uint32_t p = (uint32_t)(a[k] >> 32) & mask, fp = (uint32_t)a[k];
+      const uint32_t pf = (uint32_t)(a[k] >> 32), p = pf & mask, fp = (uint32_t)a[k];
       if (fp == 0xffffffffu) {
         atomicOr(multi_bits + (p >> 5), 1u << (p & 31));
       } else {
         atomicAnd(first_bits + (p >> 5), ~(1u << (p & 31)));
-        atomicOr(aux + p, fp);
+        aux[p] = (pf & ~IDX_MASK) | fp;  // the node's flags came along in the record's position word
       }
     }
   }
