@@ -128,7 +128,8 @@ partition_tile(const uint32_t bx, const uint32_t by, const uint32_t* __restrict_
         } else {
           l = __ldcg(leaf.words + 2 * (uint64_t)i);
         }
-        const uint32_t firsts = __ldg(leaf.first_bits + (i >> 4)) >> ((2u * i) & 31u);
+        // (no bitmap: every word is still a code, as the sharded build's replicated leaf table leaves them)
+        const uint32_t firsts = leaf.first_bits ? __ldg(leaf.first_bits + (i >> 4)) >> ((2u * i) & 31u) : 0u;
         if (!(firsts & 1u)) l = finish_leaf(l, leaf);
         if (pair && !(firsts & 2u)) r = finish_leaf(r, leaf);
         if (pair) reinterpret_cast<uint2*>(leaf.words)[i] = make_uint2(l, r);
@@ -312,9 +313,9 @@ template <int PT_THREADS>
 __global__ void __launch_bounds__(PT_THREADS, 2048 / PT_THREADS)
 partition_leaves_kernel(LeafFinish leaf, uint32_t n_cur, uint32_t n_next, unsigned long long* __restrict__ out_keys, uint32_t* __restrict__ out_pos,
                         uint32_t* __restrict__ out_count, uint32_t out_cap, int shift, int bits, uint32_t* __restrict__ aux, uint32_t* __restrict__ first_bits,
-                        uint32_t* __restrict__ multi_bits, uint32_t* __restrict__ overflow) {
+                        uint32_t* __restrict__ multi_bits, uint32_t* __restrict__ overflow, uint32_t pos_base) {
   partition_tile<true, PT_THREADS, false, false, true>(blockIdx.x, 0u, nullptr, n_cur, n_next, nullptr, nullptr, nullptr, 0u, out_keys, out_pos, out_count,
-                                                       out_cap, shift, bits, aux, first_bits, multi_bits, nullptr, nullptr, overflow, 1u, 0u, PeerDest{},
+                                                       out_cap, shift, bits, aux, first_bits, multi_bits, nullptr, nullptr, overflow, 1u, pos_base, PeerDest{},
                                                        nullptr, leaf);
 }
 
@@ -578,7 +579,7 @@ static int launch_partitions(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& pl
   if (leaf) {
     Launch l(ctx, "bucket_partition");
     partition_leaves_kernel<T><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(*leaf, n_cur, n_next, ws.keys1.ptr, ws.pos1.ptr, count1, pl.cap1, 64 - pl.b1,
-                                                                               pl.b1, aux, first_bits, multi_bits, overflow);
+                                                                               pl.b1, aux, first_bits, multi_bits, overflow, 0u);
   } else {
     Launch l(ctx, "bucket_partition");
     partition_kernel<true, T, false><<<(unsigned)ceil_div(n_next, TILE), T, smem, st>>>(
@@ -631,11 +632,17 @@ constexpr int SH_PT = 512, SH_DD = 512;
 // Step 1 of a sharded level: this rank's positions -> records in its own first-pass buckets (the owners pull them).
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
                     const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
-                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow) {
+                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow, const LeafFinish* leaf) {
   const size_t smem = pt_smem(SH_PT);
   STB_CUDA(ctx, cudaFuncSetAttribute(partition_kernel<true, SH_PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  STB_CUDA(ctx, cudaFuncSetAttribute(partition_leaves_kernel<SH_PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (n_next == 0) return STB_OK;
   Launch l(ctx, "shard_partition");
+  if (leaf) {  // the first node level: the leaf words are finished on the way
+    partition_leaves_kernel<SH_PT><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
+        *leaf, n_cur, n_next, seg_keys, seg_pos, seg_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, multi_bits, overflow, pos_base);
+    return STB_OK;
+  }
   partition_kernel<true, SH_PT, false><<<(unsigned)ceil_div(n_next, SH_PT * PT_ITEMS), SH_PT, smem, ctx.stream>>>(
       cur, n_cur, n_next, nullptr, nullptr, nullptr, 0u, seg_keys, seg_pos, seg_count, sb.cap_seg, 64 - sb.b1, sb.b1, aux, first_bits, multi_bits,
       child_first, child_multi, overflow, 1u, pos_base, PeerDest{});

@@ -89,7 +89,7 @@ int bucket_dedup_level(Ctx& ctx, BucketWorkspace& ws, const BucketPlan& plan, co
 // their counts, in its arena); the owner's split reads every rank's through `dest`.
 int shard_partition(Ctx& ctx, const ShardBuckets& sb, const uint32_t* cur, uint32_t n_cur, uint32_t n_next, uint32_t pos_base,
                     const uint32_t* child_first, const uint32_t* child_multi, uint32_t* aux, uint32_t* first_bits, uint32_t* multi_bits,
-                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow);
+                    unsigned long long* seg_keys, uint32_t* seg_pos, uint32_t* seg_count, uint32_t* overflow, const LeafFinish* leaf = nullptr);
 int shard_dedup(Ctx& ctx, const ShardBuckets& sb, BucketWorkspace& ws, uint32_t* count2, uint32_t* overflow);
 
 }  // namespace stb

@@ -703,7 +703,9 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     leaf_ids_kernel<<<(unsigned)ceil_div(canon_entries, 256), 256, 0, st>>>(s.dminpos.ptr, (uint32_t)canon_entries, s.leaf_bits.ptr, s.tilecnt.ptr, s.dids.ptr,
                                                                            s.leaves.ptr, S);
   }
-  if (n_local) {
+  // with at least one sharded node level, its partition pass finishes the leaf words on the way (bucket.cuh: LeafFinish)
+  const bool fuse_leaf = L > 1;
+  if (n_local && !fuse_leaf) {
     Launch l(s, "shard_leaf_pointers");
     leaf_pointers_kernel<<<(unsigned)ceil_div(n_local, 256), 256, 0, st>>>(ptr_cur, (uint32_t)n_local, s.dids.ptr);
   }
@@ -734,8 +736,9 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
     STB_CUDA(s, cudaMemsetAsync(multi_bits, 0, words * 4, st));
     STB_CUDA(s, cudaMemsetAsync(seg_count, 0, 512 * 4, st));
     STB_CUDA(s, cudaMemsetAsync(s.arena + s.off_ans_count, 0, STB_MAX_RANKS * 4, st));
+    const LeafFinish leaf_finish{ptr_cur, nullptr, s.dids.ptr, nullptr};
     STB_TRY(shard_partition(s, sb, ptr_cur, (uint32_t)n_cur_local, (uint32_t)n_next_local, (uint32_t)lo, child_first, child_multi, aux, first_bits,
-                            multi_bits, seg_keys, seg_pos, seg_count, s.scalars.ptr + 3));
+                            multi_bits, seg_keys, seg_pos, seg_count, s.scalars.ptr + 3, (j == 0 && fuse_leaf) ? &leaf_finish : nullptr));
     {
       Launch l(s, "peer_exchange");
       STB_TRY(s.exchange(0, seg_count, local1, local1));  // every rank's buckets are complete and the owners know their sizes: they pull them
