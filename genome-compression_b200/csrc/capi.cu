@@ -41,7 +41,23 @@ void Ctx::flush_profile() {
   pending.clear();
 }
 
+cudaError_t Ctx::copy_lane(size_t events) {
+  if (!copy_stream) {
+    const cudaError_t e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+  }
+  while (copy_events.size() < events) {
+    cudaEvent_t ev;
+    const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    copy_events.push_back(ev);
+  }
+  return cudaSuccess;
+}
+
 Ctx::~Ctx() {
+  for (auto e : copy_events) cudaEventDestroy(e);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   for (auto& p : pending) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);

@@ -348,6 +348,10 @@ struct Ctx {
   }
   cudaEvent_t get_event();
   void flush_profile();  // synchronises and folds pending events into acc
+  // a second stream for chunked host-to-device copies that later work on `stream` waits for chunk by chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  cudaError_t copy_lane(size_t events);
   ~Ctx();
 };
 

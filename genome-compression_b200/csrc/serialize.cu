@@ -522,10 +522,34 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
   const uint64_t padded = ((len + 31) & ~31ull) + DP_TILE + 64;
   STB_CUDA(t, t.staging.ensure(padded, st));
   uint8_t* d_stream = reinterpret_cast<uint8_t*>(t.staging.ptr);
-  STB_CUDA(t, cudaMemcpyAsync(d_stream, in, len, cudaMemcpyHostToDevice, st));
+  // copied in chunks on a second stream; a layer is parsed as soon as the chunks it can reach have arrived, so the
+  // parse (about a third of the copy's time) hides behind the copy
+  constexpr uint64_t COPY_CHUNK = 64ull << 20;
+  const uint64_t chunks = ceil_div(len, COPY_CHUNK);
+  STB_CUDA(t, t.copy_lane(chunks + 1));
+  STB_CUDA(t, cudaEventRecord(t.copy_events[chunks], st));  // the staging buffer is free (and allocated) at this point of `st`
+  STB_CUDA(t, cudaStreamWaitEvent(t.copy_stream, t.copy_events[chunks], 0));
+  for (uint64_t c = 0; c < chunks; ++c) {
+    const uint64_t at = c * COPY_CHUNK, n = std::min<uint64_t>(COPY_CHUNK, len - at);
+    STB_CUDA(t, cudaMemcpyAsync(d_stream + at, in + at, n, cudaMemcpyHostToDevice, t.copy_stream));
+    STB_CUDA(t, cudaEventRecord(t.copy_events[c], t.copy_stream));
+  }
   STB_CUDA(t, cudaMemsetAsync(d_stream + len, 0, padded - len, st));
+  // a damaged stream is reported only after the copies have ended: the caller's buffer must be free when a call returns
+  auto bad = [&](const std::string& what) {
+    cudaStreamSynchronize(t.copy_stream);
+    return t.fail(STB_ERR_BAD_STREAM, what);
+  };
+  int64_t waited = -1;
+  auto wait_for = [&](uint64_t end_byte) -> cudaError_t {  // `st` goes on once bytes [0, end_byte) are on the device
+    const int64_t c = (int64_t)std::min<uint64_t>(chunks - 1, (std::max<uint64_t>(end_byte, 1) - 1) / COPY_CHUNK);
+    if (c <= waited) return cudaSuccess;
+    waited = c;
+    return cudaStreamWaitEvent(st, t.copy_events[c], 0);
+  };
 
   STB_CUDA(t, t.leaves.alloc(n_leaves, st));
+  STB_CUDA(t, wait_for(o + n_leaves * (uint64_t)leaf_bytes));
   if (n_leaves) {
     Launch l(t, "parse_leaves");
     parse_leaves_kernel<<<(unsigned)ceil_div(n_leaves, 256), 256, 0, st>>>(d_stream, o, (uint32_t)n_leaves, leaf_bytes, t.leaves.ptr);
@@ -540,8 +564,8 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
   while (o + 8 <= len) {  // layers until the stream ends (:528-530)
     uint64_t count;
     read_u64(count);
-    if (count > (len - o) / 2) return t.fail(STB_ERR_BAD_STREAM, "layer size exceeds the remaining stream");
-    if (count >= IDX_MASK) return t.fail(STB_ERR_BAD_STREAM, "layer larger than the pointer format can index");
+    if (count > (len - o) / 2) return bad("layer size exceeds the remaining stream");
+    if (count >= IDX_MASK) return bad("layer larger than the pointer format can index");
     const size_t k = t.layers.size();
     t.layers.emplace_back();
     Layer& layer = t.layers.back();
@@ -551,10 +575,10 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
       std::vector<uint2> nodes(count);
       for (uint64_t i = 0; i < count; ++i) {
         uint2 nd;
-        if (!read_ptr(nd.x) || !read_ptr(nd.y)) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
+        if (!read_ptr(nd.x) || !read_ptr(nd.y)) return bad("stream ends inside a node");
         const uint32_t l = nd.x & IDX_MASK, r = nd.y & IDX_MASK;
         if ((l != IDX_MASK && l >= below) || (r != IDX_MASK && r >= below))
-          return t.fail(STB_ERR_BAD_STREAM, "a node of layer " + std::to_string(k) + " points past the end of the layer below");
+          return bad("a node of layer " + std::to_string(k) + " points past the end of the layer below");
         nodes[i] = nd;
       }
       STB_CUDA(t, cudaMemcpyAsync(layer.nodes.ptr, nodes.data(), count * sizeof(uint2), cudaMemcpyHostToDevice, st));
@@ -564,6 +588,7 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
       const uint32_t start_off = (uint32_t)(o - begin);
       const uint64_t extent = std::min<uint64_t>(len - begin, start_off + 8 * count);  // the longest the layer can be
       const uint32_t tiles = (uint32_t)ceil_div(extent, DP_TILE);
+      STB_CUDA(t, wait_for(std::min<uint64_t>(len, begin + (uint64_t)tiles * DP_TILE + 64)));
       STB_CUDA(t, tile_maps.ensure(tiles, st));
       STB_CUDA(t, tile_entry.ensure(tiles, st));
       STB_CUDA(t, cudaMemsetAsync(result.ptr, 0, 16, st));
@@ -584,15 +609,16 @@ int deserialize_tree(Tree& t, const uint8_t* in, uint64_t len) {
       STB_CUDA(t, cudaMemcpyAsync(res, result.ptr, 16, cudaMemcpyDeviceToHost, st));
       STB_CUDA(t, cudaStreamSynchronize(st));
       STB_CUDA(t, cudaGetLastError());
-      if (res[0] == 0 || res[0] > len) return t.fail(STB_ERR_BAD_STREAM, "stream ends inside a node");
-      if (res[1]) return t.fail(STB_ERR_BAD_STREAM, "a node of layer " + std::to_string(k) + " points past the end of the layer below");
+      if (res[0] == 0 || res[0] > len) return bad("stream ends inside a node");
+      if (res[1]) return bad("a node of layer " + std::to_string(k) + " points past the end of the layer below");
       o = res[0];
     }
     below = count;
   }
-  if (t.layers.empty()) return t.fail(STB_ERR_BAD_STREAM, "stream holds no node layer");
-  if ((root & IDX_MASK) >= below) return t.fail(STB_ERR_BAD_STREAM, "the root pointer does not index the top layer");
+  STB_CUDA(t, wait_for(len));  // the caller's buffer is free again when this call returns
   STB_CUDA(t, cudaStreamSynchronize(st));
+  if (t.layers.empty()) return bad("stream holds no node layer");
+  if ((root & IDX_MASK) >= below) return bad("the root pointer does not index the top layer");
   t.n_leaves = n_leaves;
   t.root = root;
   t.built = true;
