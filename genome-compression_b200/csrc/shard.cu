@@ -134,7 +134,7 @@ peer_exchange_kernel(PeerBox box, const uint32_t* __restrict__ send, uint32_t wo
     const volatile uint32_t* mine = reinterpret_cast<const volatile uint32_t*>(box.base[box.self] + box.flag_off) + peer;
     const long long t0 = clock64();
     while ((int32_t)(*mine - epoch) < 0) {
-      if (clock64() - t0 > 8000000000ll) {  // a peer that never arrives (it failed on its own): give up after seconds, not never
+      if (clock64() - t0 > 60000000000ll) {  // a peer that never arrives (it failed on its own): give up after half a minute, not never
         *timeout_flag = 1u;
         break;
       }
@@ -831,7 +831,7 @@ int shard_build(Shard& s, const char* d_body, uint64_t n_bases_total) {
   STB_CUDA(s, cudaMemcpyAsync(&timed_out, s.scalars.ptr + 6, 4, cudaMemcpyDeviceToHost, st));
   STB_CUDA(s, cudaStreamSynchronize(st));
   STB_CUDA(s, cudaGetLastError());
-  if (timed_out) return s.fail(STB_ERR_CUDA, "sharded build: a rank did not reach a level's barrier within seconds (did it fail on its own?)");
+  if (timed_out) return s.fail(STB_ERR_CUDA, "sharded build: a rank did not reach a level's barrier within half a minute (did it fail on its own?)");
   s.whole_on_root = false;
   for (uint32_t f : overflowed)
     if (f) s.whole_on_root = true;
